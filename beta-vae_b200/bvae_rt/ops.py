@@ -1,0 +1,330 @@
+"""torch.autograd.Function wrappers over the C ABI (include/bvae_b200.h).
+
+Tensors crossing these functions:
+  * activations: contiguous NHWC ``[B, H, W, C]`` in the compute dtype (fp32 or bf16);
+  * parameters / gradients: fp32 in the reference's own layout (what ``state_dict`` holds).
+Nothing here computes on the CPU or falls back to ATen for the hot ops; every call goes to
+libbvae_b200.so and raises ``BvaeError`` on failure."""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+from .lib import BF16, F32, call, query
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise lib.BvaeError("bvae_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise lib.BvaeError("bvae_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def torch_dtype(dt):
+    return torch.bfloat16 if dt == BF16 else torch.float32
+
+
+def code_of(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise lib.BvaeError(f"unsupported dtype {t.dtype}")
+
+
+def conv_out(n, stride):
+    return (n - 1) // stride + 1
+
+
+# --------------------------------------------------------------------------------------
+# weight packs (fp32 master -> compute layout), cached on the parameter version
+# --------------------------------------------------------------------------------------
+class PackCache:
+    """Compute-layout copies of the master parameters.  An entry is rebuilt when the version
+    counter or storage of any source parameter changes (optimizer steps, load_state_dict);
+    ``bump()`` invalidates everything (used by the fused optimizer, which writes parameters
+    through raw pointers)."""
+
+    def __init__(self):
+        self._d = {}
+        self._epoch = 0
+
+    def bump(self):
+        self._epoch += 1
+
+    def get(self, key, params, dt, build):
+        sig = (self._epoch,) + tuple((p._version, p.data_ptr()) for p in params)
+        ent = self._d.get((key, dt))
+        if ent is not None and ent[0] == sig:
+            return ent[1]
+        with torch.no_grad():
+            val = build()
+        self._d[(key, dt)] = (sig, val)
+        return val
+
+
+def pack_conv(w, dt, transpose, layout=0):
+    cout, cin = w.shape[0], w.shape[1]
+    k, n = (cout, cin) if transpose else (cin, cout)
+    shape = (9, k, n) if layout == 0 else (9, n, k)
+    wp = torch.empty(shape, dtype=torch_dtype(dt), device=w.device)
+    call("bvae_pack_conv_weight", _p(w), _p(wp), cout, cin, layout, 1 if transpose else 0, dt, _stream())
+    return wp
+
+
+def pack_heads(w_mu, w_lv, dt, C, P):
+    L = w_mu.shape[0]
+    wh = torch.empty((2 * L, C * P), dtype=torch_dtype(dt), device=w_mu.device)
+    call("bvae_pack_heads_weight", _p(w_mu), _p(w_lv), _p(wh), L, C, P, dt, _stream())
+    return wh
+
+
+def pack_fcdec(w, b, dt, C, P):
+    L = w.shape[1]
+    wd = torch.empty((L, C * P), dtype=torch_dtype(dt), device=w.device)
+    bd = torch.empty((C * P,), dtype=torch.float32, device=w.device)
+    call("bvae_pack_fcdec_weight", _p(w), _p(b), _p(wd), _p(bd), L, C, P, dt, _stream())
+    return wd, bd
+
+
+# --------------------------------------------------------------------------------------
+# raw op wrappers (no autograd) -- also what the unit tests drive
+# --------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, dt):
+    B, Cc, H, W = x.shape
+    y = torch.empty((B, H, W, Cc), dtype=torch_dtype(dt), device=x.device)
+    call("bvae_nchw_to_nhwc", _p(x), _p(y), B, Cc, H, W, dt, _stream())
+    return y
+
+
+def conv3x3_fprop(x, wp, bias, cout, stride, dt):
+    B, H, W, Cin = x.shape
+    y = torch.empty((B, conv_out(H, stride), conv_out(W, stride), cout), dtype=torch_dtype(dt), device=x.device)
+    call("bvae_conv3x3_fprop", _p(x), _p(wp), _p(bias), _p(y), B, H, W, Cin, cout, stride, code_of(x), dt, _stream())
+    return y
+
+
+def conv3x3_dgrad(dy, wpt, in_shape, stride):
+    B, H, W, Cin = in_shape
+    Cout = dy.shape[3]
+    dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
+    call("bvae_conv3x3_dgrad", _p(dy), _p(wpt), _p(dx), B, H, W, Cin, Cout, stride, code_of(dy), _stream())
+    return dx
+
+
+def conv3x3_wgrad(x, dy, stride, want_bias=True):
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    db = torch.empty((Cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    n = query("bvae_conv3x3_wgrad_workspace", B, H, W, Cin, Cout, stride)
+    ws = _ws(n, x.device)
+    call("bvae_conv3x3_wgrad", _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), B, H, W, Cin, Cout, stride,
+         code_of(x), code_of(dy), _stream())
+    return dw, db
+
+
+def upsample2x_fwd(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
+    call("bvae_upsample2x_fwd", _p(x), _p(y), B, H, W, Cc, code_of(x), _stream())
+    return y
+
+
+def upsample2x_bwd(dy):
+    B, H2, W2, Cc = dy.shape
+    dx = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=dy.dtype, device=dy.device)
+    call("bvae_upsample2x_bwd", _p(dy), _p(dx), B, H2 // 2, W2 // 2, Cc, code_of(dy), _stream())
+    return dx
+
+
+def gn_relu_se_fwd(y, gamma, beta, w1, b1, w2, b2):
+    B, H, W, Cc = y.shape
+    P = H * W
+    dev = y.device
+    has_se = w1 is not None
+    R = w1.shape[0] if has_se else 0
+    out = torch.empty_like(y)
+    stats = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    cpos, spos, hidden, gate = (f(B, Cc), f(B, Cc), f(B, R), f(B, Cc)) if has_se else (None,) * 4
+    ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
+    call("bvae_gn_relu_se_fwd", _p(y), _p(out), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P, Cc, R,
+         _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(ws), ws.numel(), code_of(y), _stream())
+    return out, (stats, cpos, spos, hidden, gate)
+
+
+def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved):
+    B, H, W, Cc = y.shape
+    P = H * W
+    dev = y.device
+    stats, cpos, spos, hidden, gate = saved
+    has_se = w1 is not None
+    R = w1.shape[0] if has_se else 0
+    dy = torch.empty_like(y)
+    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+    dw1, db1, dw2, db2 = ((torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2))
+                          if has_se else (None,) * 4)
+    ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
+    call("bvae_gn_relu_se_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P,
+         Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1), _p(db1),
+         _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
+    return dy, dgamma, dbeta, dw1, db1, dw2, db2
+
+
+# --------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------
+class ConvGnSeBlock(torch.autograd.Function):
+    """[bilinear x2 ->] conv3x3 -> GroupNorm(1,C) -> ReLU -> [SE]: one encoder ConvBlock or
+    decoder DeconvBlock of the reference (src/models/beta_vae.py:33-66)."""
+
+    @staticmethod
+    def forward(ctx, x, cw, cb, gw, gb, w1, b1, w2, b2, wp, wpt, stride, upsample, dt):
+        xin = upsample2x_fwd(x) if upsample else x
+        y = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt)
+        out, saved = gn_relu_se_fwd(y, gw, gb, w1, b1, w2, b2)
+        stats, cpos, spos, hidden, gate = saved
+        ctx.save_for_backward(xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate)
+        ctx.stride, ctx.upsample = stride, upsample
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate = ctx.saved_tensors
+        dout = dout.contiguous()
+        dy, dgw, dgb, dw1, db1, dw2, db2 = gn_relu_se_bwd(dout, y, gw, gb, w1, b1, w2, b2,
+                                                          (stats, cpos, spos, hidden, gate))
+        dcw, dcb = conv3x3_wgrad(xin, dy, ctx.stride)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = conv3x3_dgrad(dy, wpt, tuple(xin.shape), ctx.stride)
+            if ctx.upsample:
+                dx = upsample2x_bwd(dx)
+        return dx, dcw, dcb, dgw, dgb, dw1, db1, dw2, db2, None, None, None, None, None
+
+
+class HeadsReparamKL(torch.autograd.Function):
+    """fc_mu/fc_logvar + clamp + z = mu + eps*exp(logvar/2) + KL statistics + KL-side objective
+    (src/models/beta_vae.py:137-150, 219-253).  Returns (mu, logvar, z, kl_per_dim, scalars)
+    with scalars = [kl_mean, kl_effective, objective, latent_reg]."""
+
+    @staticmethod
+    def forward(ctx, h, w_mu, b_mu, w_lv, b_lv, eps, wh, lo, hi, beta, use_cap, cap, cap_w, fb, reg, det, dt):
+        B, Hs, Ws, Cc = h.shape
+        P, F = Hs * Ws, Hs * Ws * Cc
+        L = w_mu.shape[0]
+        dev = h.device
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        mu, logvar, z, klpd, sc = f(B, L), f(B, L), f(B, L), f(L), f(4)
+        lv_pass = torch.empty((B, L), dtype=torch.uint8, device=dev)
+        ws = _ws(query("bvae_heads_workspace", B, L, F), dev)
+        call("bvae_heads_reparam_kl_fwd", _p(h), _p(wh), _p(b_mu), _p(b_lv), _p(eps), lo, hi, beta, int(use_cap), cap,
+             cap_w, fb, reg, int(det), _p(mu), _p(logvar), _p(z), _p(klpd), _p(sc), _p(lv_pass), _p(ws), ws.numel(),
+             B, L, F, dt, _stream())
+        ctx.save_for_backward(h, wh, eps, mu, logvar, klpd, sc, lv_pass)
+        ctx.cfg = (beta, int(use_cap), cap, cap_w, fb, reg, int(det), dt, Cc, P, L)
+        ctx.mark_non_differentiable(klpd)
+        ctx.set_materialize_grads(False)
+        return mu, logvar, z, klpd, sc
+
+    @staticmethod
+    def backward(ctx, g_mu, g_lv, g_z, _g_klpd, g_sc):
+        h, wh, eps, mu, logvar, klpd, sc, lv_pass = ctx.saved_tensors
+        beta, use_cap, cap, cap_w, fb, reg, det, dt, Cc, P, L = ctx.cfg
+        B = h.shape[0]
+        dev = h.device
+        c = lambda t: None if t is None else t.contiguous().float()
+        g_mu, g_lv, g_z, g_sc = c(g_mu), c(g_lv), c(g_z), c(g_sc)
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        dwm = torch.empty((L, Cc * P), dtype=torch.float32, device=dev)
+        dwl = torch.empty((L, Cc * P), dtype=torch.float32, device=dev)
+        dbm = torch.empty((L,), dtype=torch.float32, device=dev)
+        dbl = torch.empty((L,), dtype=torch.float32, device=dev)
+        ws = _ws(query("bvae_heads_workspace", B, L, Cc * P), dev)
+        call("bvae_heads_reparam_kl_bwd", _p(h), _p(wh), _p(eps), _p(mu), _p(logvar), _p(klpd), _p(sc), _p(lv_pass),
+             _p(g_mu), _p(g_lv), _p(g_z), _p(g_sc), beta, use_cap, cap, cap_w, fb, reg, det, _p(dh), _p(dwm), _p(dwl),
+             _p(dbm), _p(dbl), _p(ws), ws.numel(), B, L, Cc, P, dt, _stream())
+        return (dh, dwm, dbm, dwl, dbl) + (None,) * 12
+
+
+class FcDec(torch.autograd.Function):
+    """Optional latent clamp + fc_dec, output NHWC [B, Hs, Ws, C] (src/models/beta_vae.py:153-161)."""
+
+    @staticmethod
+    def forward(ctx, z, w, b, wd, bd, z_clamp, dt, Cc, Hs, Ws):
+        B, L = z.shape
+        z = z.contiguous().float()
+        h0 = torch.empty((B, Hs, Ws, Cc), dtype=torch_dtype(dt), device=z.device)
+        call("bvae_fc_dec_fwd", _p(z), _p(wd), _p(bd), _p(h0), z_clamp, B, L, Cc * Hs * Ws, dt, _stream())
+        ctx.save_for_backward(z, wd)
+        ctx.cfg = (z_clamp, dt, Cc, Hs * Ws)
+        return h0
+
+    @staticmethod
+    def backward(ctx, dh0):
+        z, wd = ctx.saved_tensors
+        z_clamp, dt, Cc, P = ctx.cfg
+        B, L = z.shape
+        dev = z.device
+        dh0 = dh0.contiguous()
+        dz = torch.empty((B, L), dtype=torch.float32, device=dev)
+        dw = torch.empty((Cc * P, L), dtype=torch.float32, device=dev)
+        db = torch.empty((Cc * P,), dtype=torch.float32, device=dev)
+        ws = _ws(query("bvae_fc_dec_workspace", B, L, Cc * P), dev)
+        call("bvae_fc_dec_bwd", _p(dh0), _p(z), _p(wd), z_clamp, _p(dz), _p(dw), _p(db), _p(ws), ws.numel(), B, L, Cc,
+             P, dt, _stream())
+        return (dz, dw, db) + (None,) * 7
+
+
+class FinalConvSigmoidRecon(torch.autograd.Function):
+    """final_conv + sigmoid + reconstruction loss (src/models/beta_vae.py:163-164, 185-192).
+    Returns (recon [B,Co,H,W] fp32, loss scalar = sum(elementwise)/B)."""
+
+    @staticmethod
+    def forward(ctx, h, w, b, target, loss_type):
+        B, H, W, Cc = h.shape
+        Co = w.shape[0]
+        dev = h.device
+        recon = torch.empty((B, Co, H, W), dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        if target is not None:
+            target = target.contiguous().float()
+        ws = _ws(query("bvae_finalconv_workspace", B, H, W, Cc, Co), dev)
+        call("bvae_finalconv_sigmoid_recon_fwd", _p(h), _p(w), _p(b), _p(target), _p(recon), _p(loss), loss_type,
+             _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
+        ctx.save_for_backward(h, w, recon, target)
+        ctx.loss_type = loss_type
+        ctx.set_materialize_grads(False)
+        if target is None:
+            ctx.mark_non_differentiable(loss)
+        return recon, loss
+
+    @staticmethod
+    def backward(ctx, g_recon, g_loss):
+        h, w, recon, target = ctx.saved_tensors
+        B, H, W, Cc = h.shape
+        Co = w.shape[0]
+        dev = h.device
+        if g_recon is not None:
+            g_recon = g_recon.contiguous().float()
+        if g_loss is not None:
+            g_loss = g_loss.contiguous().float()
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty((Co,), dtype=torch.float32, device=dev)
+        ws = _ws(query("bvae_finalconv_workspace", B, H, W, Cc, Co), dev)
+        call("bvae_finalconv_sigmoid_recon_bwd", _p(h), _p(w), _p(recon), _p(target), _p(g_recon), _p(g_loss), _p(dh),
+             _p(dw), _p(db), ctx.loss_type, _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
+        return dh, dw, db, None, None

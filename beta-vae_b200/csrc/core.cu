@@ -1,0 +1,282 @@
+// Error plumbing, device query, weight packing, layout glue, fused clip+Adam.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace bvae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return BVAE_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels
+// ---------------------------------------------------------------------------------------------
+// dst index space is [9][D1][D2]; (k, n) -> (ci, co) or (co, ci) per `transpose`;
+// layout 0: [t][k][n]; layout 1: [t][n][k].
+template <typename T>
+__global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp, int Cout, int Cin, int layout,
+                                 int transpose) {
+  const int K = transpose ? Cout : Cin, N = transpose ? Cin : Cout;
+  const long long total = 9LL * K * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / ((long long)K * N));
+    const long long rem = i % ((long long)K * N);
+    int k, n;
+    if (layout == 0) {
+      k = (int)(rem / N);
+      n = (int)(rem % N);
+    } else {
+      n = (int)(rem / K);
+      k = (int)(rem % K);
+    }
+    const int ci = transpose ? n : k, co = transpose ? k : n;
+    wp[i] = Elem<T>::from_f(w[((size_t)co * Cin + ci) * 9 + t]);
+  }
+}
+
+// wh[r][p*C + c] = (r < L ? w_mu : w_lv)[r % L][c*P + p]
+template <typename T>
+__global__ void pack_heads_kernel(const float* __restrict__ wmu, const float* __restrict__ wlv, T* __restrict__ wh,
+                                  int L, int C, int P) {
+  const long long F = (long long)C * P, total = 2LL * L * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / F);
+    const long long f = i % F;
+    const int p = (int)(f / C), c = (int)(f % C);
+    const float* src = (r < L) ? wmu : wlv;
+    wh[i] = Elem<T>::from_f(src[(size_t)(r % L) * F + (size_t)c * P + p]);
+  }
+}
+
+// wd[l][p*C + c] = w[(c*P + p)][l];  bd[p*C + c] = b[c*P + p]
+template <typename T>
+__global__ void pack_fcdec_kernel(const float* __restrict__ w, const float* __restrict__ b, T* __restrict__ wd,
+                                  float* __restrict__ bd, int L, int C, int P) {
+  const long long F = (long long)C * P, total = (long long)L * F;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i / F);
+    const long long f = i % F;
+    const int p = (int)(f / C), c = (int)(f % C);
+    const size_t fr = (size_t)c * P + p;
+    wd[i] = Elem<T>::from_f(w[fr * L + l]);
+    if (l == 0) bd[f] = b[fr];
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int C, int HW) {
+  const long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bp = i / C;
+    const int p = (int)(bp % HW);
+    const int b = (int)(bp / HW);
+    y[i] = Elem<T>::from_f(x[((size_t)b * C + c) * HW + p]);
+  }
+}
+
+static inline int grid_for(long long total, int threads = 256) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = 8LL * num_sms();
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip + Adam
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, size_t n,
+                                                            double* __restrict__ part) {
+  __shared__ double red[32];
+  float acc = 0.f;
+  const size_t n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    acc = fmaf(v.x, v.x, acc);
+    acc = fmaf(v.y, v.y, acc);
+    acc = fmaf(v.z, v.z, acc);
+    acc = fmaf(v.w, v.w, acc);
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) acc = fmaf(g[i], g[i], acc);
+  const double s = block_sum((double)acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const double* __restrict__ part, int n,
+                                                          float* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = (float)acc;
+}
+
+// torch.optim.Adam / AdamW single-tensor semantics (amsgrad=False, maximize=False):
+//   g' = g*clip;  [Adam: g' += wd*p | AdamW: p *= 1 - lr*wd]
+//   m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2
+//   p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256)
+    adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                size_t n, const float* __restrict__ sumsq, float grad_scale, float max_norm, float lr, float b1,
+                float b2, float eps, float wd, int decoupled, float bc1, float bc2_sqrt) {
+  float clip = grad_scale;
+  if (max_norm > 0.f && sumsq) {
+    const float total = sqrtf(sumsq[0]) * grad_scale;
+    const float c = max_norm / (total + 1e-6f);  // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    clip *= fminf(c, 1.0f);
+  }
+  const float step = lr / bc1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * clip, pi = p[i];
+    if (wd != 0.f) {
+      if (decoupled)
+        pi *= 1.f - lr * wd;
+      else
+        gi = fmaf(wd, pi, gi);
+    }
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+}  // namespace bvae
+
+using namespace bvae;
+
+extern "C" int bvae_version(void) { return 100; }
+extern "C" const char* bvae_last_error(void) { return g_err; }
+
+extern "C" int bvae_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int bvae_pack_conv_weight(const float* w, void* wp, int Cout, int Cin, int layout, int transpose,
+                                     int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(w && wp && Cout > 0 && Cin > 0, BVAE_ERR_ARG, "pack_conv_weight: bad argument");
+  BVAE_REQUIRE(layout == 0 || layout == 1, BVAE_ERR_ARG, "pack_conv_weight: layout %d", layout);
+  const long long total = 9LL * Cout * Cin;
+  if (dtype == BVAE_F32)
+    pack_conv_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(w, (float*)wp, Cout, Cin, layout, transpose);
+  else if (dtype == BVAE_BF16)
+    pack_conv_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, as_stream(stream)>>>(w, (__nv_bfloat16*)wp, Cout, Cin,
+                                                                                   layout, transpose);
+  else
+    BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_conv_weight: dtype %d", dtype);
+  BVAE_LAUNCH_CHECK("pack_conv_weight");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_pack_heads_weight(const float* w_mu, const float* w_logvar, void* wh, int L, int C, int P,
+                                      int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(w_mu && w_logvar && wh && L > 0 && C > 0 && P > 0, BVAE_ERR_ARG, "pack_heads_weight: bad argument");
+  const long long total = 2LL * L * C * P;
+  if (dtype == BVAE_F32)
+    pack_heads_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(w_mu, w_logvar, (float*)wh, L, C, P);
+  else if (dtype == BVAE_BF16)
+    pack_heads_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, as_stream(stream)>>>(w_mu, w_logvar,
+                                                                                    (__nv_bfloat16*)wh, L, C, P);
+  else
+    BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_heads_weight: dtype %d", dtype);
+  BVAE_LAUNCH_CHECK("pack_heads_weight");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_pack_fcdec_weight(const float* w, const float* b, void* wd, float* bd, int L, int C, int P,
+                                      int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(w && b && wd && bd && L > 0 && C > 0 && P > 0, BVAE_ERR_ARG, "pack_fcdec_weight: bad argument");
+  const long long total = (long long)L * C * P;
+  if (dtype == BVAE_F32)
+    pack_fcdec_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(w, b, (float*)wd, bd, L, C, P);
+  else if (dtype == BVAE_BF16)
+    pack_fcdec_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, as_stream(stream)>>>(w, b, (__nv_bfloat16*)wd, bd, L,
+                                                                                    C, P);
+  else
+    BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_fcdec_weight: dtype %d", dtype);
+  BVAE_LAUNCH_CHECK("pack_fcdec_weight");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_nchw_to_nhwc(const float* x, void* y, int B, int C, int H, int W, int dtype,
+                                 bvae_stream_t stream) {
+  BVAE_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, BVAE_ERR_ARG, "nchw_to_nhwc: bad argument");
+  const long long total = (long long)B * C * H * W;
+  if (dtype == BVAE_F32)
+    nchw_to_nhwc_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (float*)y, B, C, H * W);
+  else if (dtype == BVAE_BF16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)y, B, C,
+                                                                                      H * W);
+  else
+    BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "nchw_to_nhwc: dtype %d", dtype);
+  BVAE_LAUNCH_CHECK("nchw_to_nhwc");
+  return BVAE_OK;
+}
+
+static constexpr int kSumsqBlocks = 592;  // 4 CTAs per SM on 148 SMs
+
+extern "C" size_t bvae_adam_workspace(size_t n) {
+  (void)n;
+  return kSumsqBlocks * sizeof(double);
+}
+
+extern "C" int bvae_grad_sumsq(const float* g, size_t n, float* sumsq_out, void* ws, size_t ws_bytes,
+                               bvae_stream_t stream) {
+  BVAE_REQUIRE(g && sumsq_out && ws, BVAE_ERR_ARG, "grad_sumsq: null pointer");
+  BVAE_REQUIRE(ws_bytes >= bvae_adam_workspace(n), BVAE_ERR_WORKSPACE, "grad_sumsq: workspace too small");
+  BVAE_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, BVAE_ERR_ARG, "grad_sumsq: g must be 16-byte aligned");
+  sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, as_stream(stream)>>>(g, n, (double*)ws);
+  BVAE_LAUNCH_CHECK("grad_sumsq");
+  sumsq_final_kernel<<<1, 256, 0, as_stream(stream)>>>((const double*)ws, kSumsqBlocks, sumsq_out);
+  BVAE_LAUNCH_CHECK("grad_sumsq_final");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_adam_clip_step(float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
+                                   float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                                   float weight_decay, int decoupled_wd, int step, bvae_stream_t stream) {
+  BVAE_REQUIRE(p && g && m && v && n > 0 && step >= 1, BVAE_ERR_ARG, "adam_clip_step: bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for((long long)n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, sumsq, grad_scale, max_norm, lr,
+                                                                    beta1, beta2, eps, weight_decay, decoupled_wd,
+                                                                    (float)bc1, (float)sqrt(bc2));
+  BVAE_LAUNCH_CHECK("adam_clip_step");
+  return BVAE_OK;
+}

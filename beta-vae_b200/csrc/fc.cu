@@ -1,0 +1,489 @@
+// Latent heads (fc_mu, fc_logvar) + clamp + reparameterisation + KL + KL-side objective,
+// and fc_dec; forward and backward.
+//
+// Replaces, from the reference: the two nn.Linear heads and torch.clamp in BetaVAE.encode
+// (src/models/beta_vae.py:137-145), reparameterize (:147-150), the KL / free-bits / capacity /
+// latent-reg arithmetic of BetaVAE.loss (:219-253), fc_dec and the latent clamp in decode
+// (:153-161), plus everything autograd derives for them.
+//
+// Two GEMM shapes cover all six products.  F = C*P (32768 for the default config) is the
+// long axis, the other two (batch, 2L) are short:
+//   reduce-F ("tall"):  out[m][n] = sum_f X[m][f] * W[n][f]       heads fwd, fc_dec dz
+//       split over F into chunks; fp32 partials [chunk][m][n]; a finalize kernel sums the
+//       chunks in a fixed order (deterministic) and applies the fused epilogue.
+//   wide-F:             out[m][f] = sum_k A[k or m][..] * Bm[k][f]  heads dh / dW, fc_dec fwd / dW
+//       K is tiny (L, 2L or B); every CTA streams a 128-feature slab of Bm exactly once.
+// Activations use NHWC feature order f' = p*C + c; master parameters / gradients use the
+// reference's NCHW order f = c*P + p.  The permutation is folded into the pack kernels
+// (core.cu) and into the store addressing of the wide-F kernel.
+#include "common.cuh"
+
+namespace bvae {
+
+// ------------------------------------------------------------------------------------------
+// reduce-F
+// ------------------------------------------------------------------------------------------
+static constexpr int RF_CHUNK = 128;  // features per CTA
+static constexpr int RF_MT = 32;      // rows (batch) per CTA
+static constexpr int RF_NT = 32;      // output columns per inner tile
+static constexpr int RF_LD = RF_CHUNK + 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) fc_reduce_f_kernel(const T* __restrict__ X, const T* __restrict__ Wm,
+                                                          float* __restrict__ part, int M, int N, int F) {
+  __shared__ __align__(16) float Xs[RF_MT][RF_LD];
+  __shared__ __align__(16) float Ws[RF_NT][RF_LD];
+  const int chunk = blockIdx.x, m0 = blockIdx.y * RF_MT;
+  const int f0 = chunk * RF_CHUNK;
+  const int tid = threadIdx.x;
+  // X tile: 32 rows x RF_CHUNK features
+  for (int i = tid; i < RF_MT * RF_CHUNK; i += 256) {
+    const int r = i / RF_CHUNK, f = i % RF_CHUNK;
+    float v = 0.f;
+    if (m0 + r < M && f0 + f < F) v = Elem<T>::to_f(X[(size_t)(m0 + r) * F + f0 + f]);
+    Xs[r][f] = v;
+  }
+  const int mr = tid >> 3, nq = tid & 7;  // row mr, columns nq + 8*j
+  for (int n0 = 0; n0 < N; n0 += RF_NT) {
+    __syncthreads();
+    for (int i = tid; i < RF_NT * RF_CHUNK; i += 256) {
+      const int r = i / RF_CHUNK, f = i % RF_CHUNK;
+      float v = 0.f;
+      if (n0 + r < N && f0 + f < F) v = Elem<T>::to_f(Wm[(size_t)(n0 + r) * F + f0 + f]);
+      Ws[r][f] = v;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int f = 0; f < RF_CHUNK; f += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(&Xs[mr][f]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(&Ws[nq + 8 * j][f]);
+        acc[j] = fmaf(xv.x, wv.x, acc[j]);
+        acc[j] = fmaf(xv.y, wv.y, acc[j]);
+        acc[j] = fmaf(xv.z, wv.z, acc[j]);
+        acc[j] = fmaf(xv.w, wv.w, acc[j]);
+      }
+    }
+    if (m0 + mr < M) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + nq + 8 * j;
+        if (n < N) part[((size_t)chunk * M + m0 + mr) * N + n] = acc[j];
+      }
+    }
+  }
+}
+
+template <typename T>
+static int reduce_f_launch(const void* X, const void* Wm, float* part, int M, int N, int F, cudaStream_t st) {
+  dim3 grid(cdiv(F, RF_CHUNK), cdiv(M, RF_MT));
+  fc_reduce_f_kernel<T><<<grid, 256, 0, st>>>((const T*)X, (const T*)Wm, part, M, N, F);
+  BVAE_LAUNCH_CHECK("fc_reduce_f");
+  return BVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// wide-F
+// ------------------------------------------------------------------------------------------
+struct FcWide {
+  const float* A;          // element (m, k) at A[m*a_sm + k*a_sk]
+  long long a_sm, a_sk;
+  int M, K;
+  int ones_row;            // row index whose A entries are all 1 (bias-gradient row), or -1
+  float a_clamp;           // > 0: A values are clamped to [-a_clamp, a_clamp] on load (latent clamp)
+  const void* Bm;          // [K][F]
+  int F;
+  const float* bias;       // [F] added to every row, or NULL
+  void* out0;              // rows m <  split: out0[m*o0_sm + g(f)*o0_sf]
+  long long o0_sm, o0_sf;
+  void* out1;              // rows m >= split: out1[(m-split)*o1_sm + g(f)*o1_sf]
+  long long o1_sm, o1_sf;
+  int split;
+  int permC, permP;        // g(f) = (f % C)*P + f / C when permC > 0 else f
+};
+
+static constexpr int WF_MT = 32, WF_FT = 128, WF_KT = 16;
+
+template <typename TB, typename TO>
+__global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
+  __shared__ __align__(16) float As[WF_KT][WF_MT + 4];
+  __shared__ __align__(16) float Bs[WF_KT][WF_FT + 4];
+  const TB* __restrict__ Bm = reinterpret_cast<const TB*>(p.Bm);
+  const int tid = threadIdx.x;
+  const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * WF_MT;
+  const int ty = tid >> 5, tx = tid & 31;  // rows ty*4..+3, features tx*4..+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += WF_KT) {
+    __syncthreads();
+    for (int i = tid; i < WF_KT * WF_MT; i += 256) {
+      const int k = i / WF_MT, m = i % WF_MT;
+      float v = 0.f;
+      if (k0 + k < p.K && m0 + m < p.M)
+        v = (m0 + m == p.ones_row) ? 1.f : p.A[(size_t)(m0 + m) * p.a_sm + (size_t)(k0 + k) * p.a_sk];
+      if (p.a_clamp > 0.f && m0 + m != p.ones_row) v = fminf(fmaxf(v, -p.a_clamp), p.a_clamp);
+      As[k][m] = v;
+    }
+    for (int i = tid; i < WF_KT * WF_FT; i += 256) {
+      const int k = i / WF_FT, f = i % WF_FT;
+      float v = 0.f;
+      if (k0 + k < p.K && f0 + f < p.F) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + f0 + f]);
+      Bs[k][f] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WF_KT; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    const bool lo = m < p.split;
+    TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
+    const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
+    const long long mm = lo ? m : m - p.split;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = f0 + tx * 4 + j;
+      if (f >= p.F) continue;
+      const long long g = p.permC > 0 ? (long long)(f % p.permC) * p.permP + f / p.permC : f;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[f];
+      base[mm * sm + g * sf] = Elem<TO>::from_f(v);
+    }
+  }
+}
+
+template <typename TB, typename TO>
+static int wide_f_launch(const FcWide& p, cudaStream_t st) {
+  dim3 grid(cdiv(p.F, WF_FT), cdiv(p.M, WF_MT));
+  fc_wide_f_kernel<TB, TO><<<grid, 256, 0, st>>>(p);
+  BVAE_LAUNCH_CHECK("fc_wide_f");
+  return BVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// heads: finalize kernels
+// ------------------------------------------------------------------------------------------
+// grid = B, block = 2L threads (rounded up to a warp multiple): sum the F-chunks, add bias, clamp,
+// reparameterise, per-element KL.
+__global__ void heads_finalize_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ b_mu,
+                                      const float* __restrict__ b_lv, const float* __restrict__ eps, float lo,
+                                      float hi, int deterministic, float* __restrict__ mu, float* __restrict__ logvar,
+                                      float* __restrict__ z, float* __restrict__ kl_elem,
+                                      uint8_t* __restrict__ lv_pass, int B, int L) {
+  const int b = blockIdx.x;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    float m = b_mu[l], v = b_lv[l];
+    for (int c = 0; c < nchunks; ++c) {
+      const float* row = part + ((size_t)c * B + b) * 2 * L;
+      m += row[l];
+      v += row[L + l];
+    }
+    const bool pass = (v >= lo) && (v <= hi);  // torch.clamp: gradient 1 inside [lo, hi], 0 outside
+    const float lv = fminf(fmaxf(v, lo), hi);
+    const size_t o = (size_t)b * L + l;
+    mu[o] = m;
+    logvar[o] = lv;
+    lv_pass[o] = pass ? 1 : 0;
+    if (deterministic || eps == nullptr) {
+      z[o] = m;
+      kl_elem[o] = 0.f;
+    } else {
+      z[o] = fmaf(eps[o], expf(0.5f * lv), m);
+      kl_elem[o] = -0.5f * (1.f + lv - m * m - expf(lv));
+    }
+  }
+}
+
+// single CTA: kl_per_dim = mean_b kl_elem; scalars = {kl_mean, kl_effective, objective, latent_reg}
+__global__ void __launch_bounds__(256)
+    heads_kl_kernel(const float* __restrict__ kl_elem, const float* __restrict__ mu, float beta, int use_capacity,
+                    float capacity, float capacity_weight, float free_bits, float reg_lambda, int deterministic,
+                    float* __restrict__ kl_per_dim, float* __restrict__ scalars, int B, int L) {
+  __shared__ float red[32];
+  float klsum = 0.f, kleff = 0.f;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += kl_elem[(size_t)b * L + l];
+    const float pd = acc / (float)B;
+    kl_per_dim[l] = pd;
+    klsum += pd;
+    kleff += (free_bits > 0.f && !use_capacity) ? fmaxf(pd, free_bits) : pd;
+  }
+  float musq = 0.f;
+  if (reg_lambda > 0.f)
+    for (int i = threadIdx.x; i < B * L; i += blockDim.x) musq = fmaf(mu[i], mu[i], musq);
+  klsum = block_sum(klsum, red);
+  kleff = block_sum(kleff, red);
+  musq = block_sum(musq, red);
+  if (threadIdx.x == 0) {
+    const float reg = reg_lambda > 0.f ? reg_lambda * musq / ((float)B * (float)L) : 0.f;
+    float obj;
+    if (deterministic) {
+      klsum = 0.f;
+      kleff = 0.f;
+      obj = reg;
+    } else if (use_capacity) {
+      obj = capacity_weight * fabsf(klsum - capacity) + reg;
+    } else {
+      obj = beta * kleff + reg;
+    }
+    scalars[0] = klsum;
+    scalars[1] = kleff;
+    scalars[2] = obj;
+    scalars[3] = reg;
+  }
+}
+
+// grid = B: D[b][0..L) = d mu, D[b][L..2L) = d (pre-clamp logvar)
+__global__ void heads_bwd_prep_kernel(const float* __restrict__ eps, const float* __restrict__ mu,
+                                      const float* __restrict__ logvar, const float* __restrict__ kl_per_dim,
+                                      const float* __restrict__ scalars, const uint8_t* __restrict__ lv_pass,
+                                      const float* __restrict__ g_mu, const float* __restrict__ g_lv,
+                                      const float* __restrict__ g_z, const float* __restrict__ g_sc, float beta,
+                                      int use_capacity, float capacity, float capacity_weight, float free_bits,
+                                      float reg_lambda, int deterministic, float* __restrict__ D, int B, int L) {
+  const int b = blockIdx.x;
+  const float g_klmean = g_sc ? g_sc[0] : 0.f;
+  const float g_obj = g_sc ? g_sc[2] : 0.f;
+  const float invB = 1.f / (float)B;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const size_t o = (size_t)b * L + l;
+    const float m = mu[o], lv = logvar[o];
+    float dm = g_mu ? g_mu[o] : 0.f;
+    float dl = g_lv ? g_lv[o] : 0.f;
+    const float gz = g_z ? g_z[o] : 0.f;
+    dm += gz;
+    if (reg_lambda > 0.f) dm = fmaf(g_obj * reg_lambda * 2.f / ((float)B * (float)L), m, dm);
+    if (!deterministic && eps != nullptr) {
+      float c;  // d(objective + kl_mean terms) / d kl_elem[b][l]
+      if (use_capacity) {
+        const float d = scalars[0] - capacity;
+        const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        c = g_obj * capacity_weight * sgn * invB;
+      } else if (free_bits > 0.f) {
+        c = (kl_per_dim[l] >= free_bits) ? g_obj * beta * invB : 0.f;
+      } else {
+        c = g_obj * beta * invB;
+      }
+      c += g_klmean * invB;
+      dm = fmaf(c, m, dm);                             // d kl_elem / d mu = mu
+      dl += gz * eps[o] * 0.5f * expf(0.5f * lv);      // z = mu + eps*exp(lv/2)
+      dl = fmaf(c, 0.5f * (expf(lv) - 1.f), dl);       // d kl_elem / d lv = (e^lv - 1)/2
+    }
+    if (!lv_pass[o]) dl = 0.f;
+    D[(size_t)b * 2 * L + l] = dm;
+    D[(size_t)b * 2 * L + L + l] = dl;
+  }
+}
+
+__global__ void heads_db_kernel(const float* __restrict__ D, float* __restrict__ db_mu, float* __restrict__ db_lv,
+                                int B, int L) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 2 * L) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += D[(size_t)b * 2 * L + n];
+  if (n < L)
+    db_mu[n] = acc;
+  else
+    db_lv[n - L] = acc;
+}
+
+// dz[b][l] = sum_chunks part[chunk][b][l], zeroed where the latent clamp saturated
+__global__ void fcdec_dz_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ z, float clamp,
+                                float* __restrict__ dz, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < nchunks; ++c) acc += part[(size_t)c * n + i];
+    if (clamp > 0.f && (z[i] < -clamp || z[i] > clamp)) acc = 0.f;
+    dz[i] = acc;
+  }
+}
+
+struct HeadsWs {
+  float* part;     // [nchunks][B][2L]
+  float* kl_elem;  // [B][L]
+  float* D;        // [B][2L]
+  size_t bytes;
+};
+static HeadsWs heads_ws_carve(void* base, int B, int L, int F) {
+  HeadsWs w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  w.part = reinterpret_cast<float*>(take((size_t)cdiv(F, RF_CHUNK) * B * 2 * L * sizeof(float)));
+  w.kl_elem = reinterpret_cast<float*>(take((size_t)B * L * sizeof(float)));
+  w.D = reinterpret_cast<float*>(take((size_t)B * 2 * L * sizeof(float)));
+  w.bytes = off;
+  return w;
+}
+
+struct FcDecWs {
+  float* part;  // [nchunks][B][L]
+  size_t bytes;
+};
+static FcDecWs fcdec_ws_carve(void* base, int B, int L, int F) {
+  FcDecWs w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  w.part = reinterpret_cast<float*>(take((size_t)cdiv(F, RF_CHUNK) * B * L * sizeof(float)));
+  w.bytes = off;
+  return w;
+}
+
+static inline int warp_round(int n) {
+  int t = (n + 31) / 32 * 32;
+  return t > 256 ? 256 : (t < 32 ? 32 : t);
+}
+
+}  // namespace bvae
+
+using namespace bvae;
+
+extern "C" size_t bvae_heads_workspace(int B, int L, int F) {
+  if (B <= 0 || L <= 0 || F <= 0) return 0;
+  return heads_ws_carve(nullptr, B, L, F).bytes;
+}
+
+extern "C" int bvae_heads_reparam_kl_fwd(const void* h, const void* wh, const float* b_mu, const float* b_logvar,
+                                         const float* eps, float lv_lo, float lv_hi, float beta, int use_capacity,
+                                         float capacity, float capacity_weight, float free_bits, float reg_lambda,
+                                         int deterministic, float* mu, float* logvar, float* z, float* kl_per_dim,
+                                         float* scalars, uint8_t* lv_pass, void* ws, size_t ws_bytes, int B, int L,
+                                         int F, int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(h && wh && b_mu && b_logvar && mu && logvar && z && kl_per_dim && scalars && lv_pass && ws,
+               BVAE_ERR_ARG, "heads_fwd: null pointer");
+  BVAE_REQUIRE(B > 0 && L > 0 && F > 0, BVAE_ERR_ARG, "heads_fwd: empty shape");
+  BVAE_REQUIRE(ws_bytes >= bvae_heads_workspace(B, L, F), BVAE_ERR_WORKSPACE, "heads_fwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  HeadsWs w = heads_ws_carve(ws, B, L, F);
+  int rc;
+  if (dtype == BVAE_F32)
+    rc = reduce_f_launch<float>(h, wh, w.part, B, 2 * L, F, st);
+  else if (dtype == BVAE_BF16)
+    rc = reduce_f_launch<__nv_bfloat16>(h, wh, w.part, B, 2 * L, F, st);
+  else
+    BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "heads_fwd: dtype %d", dtype);
+  if (rc != BVAE_OK) return rc;
+  heads_finalize_kernel<<<B, warp_round(L), 0, st>>>(w.part, cdiv(F, RF_CHUNK), b_mu, b_logvar, eps, lv_lo, lv_hi,
+                                                    deterministic, mu, logvar, z, w.kl_elem, lv_pass, B, L);
+  BVAE_LAUNCH_CHECK("heads_finalize");
+  heads_kl_kernel<<<1, 256, 0, st>>>(w.kl_elem, mu, beta, use_capacity, capacity, capacity_weight, free_bits,
+                                     reg_lambda, (deterministic || eps == nullptr) ? 1 : 0, kl_per_dim, scalars, B, L);
+  BVAE_LAUNCH_CHECK("heads_kl");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_heads_reparam_kl_bwd(const void* h, const void* wh, const float* eps, const float* mu,
+                                         const float* logvar, const float* kl_per_dim, const float* scalars,
+                                         const uint8_t* lv_pass, const float* g_mu, const float* g_logvar,
+                                         const float* g_z, const float* g_scalars, float beta, int use_capacity,
+                                         float capacity, float capacity_weight, float free_bits, float reg_lambda,
+                                         int deterministic, void* dh, float* dw_mu, float* dw_logvar, float* db_mu,
+                                         float* db_logvar, void* ws, size_t ws_bytes, int B, int L, int C, int P,
+                                         int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(h && wh && mu && logvar && kl_per_dim && scalars && lv_pass && dw_mu && dw_logvar && db_mu &&
+                   db_logvar && ws,
+               BVAE_ERR_ARG, "heads_bwd: null pointer");
+  BVAE_REQUIRE(B > 0 && L > 0 && C > 0 && P > 0, BVAE_ERR_ARG, "heads_bwd: empty shape");
+  const int F = C * P;
+  BVAE_REQUIRE(ws_bytes >= bvae_heads_workspace(B, L, F), BVAE_ERR_WORKSPACE, "heads_bwd: workspace too small");
+  BVAE_REQUIRE(dtype == BVAE_F32 || dtype == BVAE_BF16, BVAE_ERR_UNSUPPORTED, "heads_bwd: dtype %d", dtype);
+  cudaStream_t st = as_stream(stream);
+  HeadsWs w = heads_ws_carve(ws, B, L, F);
+  heads_bwd_prep_kernel<<<B, warp_round(L), 0, st>>>(eps, mu, logvar, kl_per_dim, scalars, lv_pass, g_mu, g_logvar,
+                                                    g_z, g_scalars, beta, use_capacity, capacity, capacity_weight,
+                                                    free_bits, reg_lambda, (deterministic || eps == nullptr) ? 1 : 0,
+                                                    w.D, B, L);
+  BVAE_LAUNCH_CHECK("heads_bwd_prep");
+  int rc = BVAE_OK;
+  if (dh) {  // dh[b][f'] = sum_n D[b][n] * wh[n][f']
+    FcWide p;
+    p.A = w.D; p.a_sm = 2 * L; p.a_sk = 1; p.M = B; p.K = 2 * L; p.ones_row = -1; p.a_clamp = 0.f;
+    p.Bm = wh; p.F = F; p.bias = nullptr;
+    p.out0 = dh; p.o0_sm = F; p.o0_sf = 1; p.out1 = dh; p.o1_sm = F; p.o1_sf = 1; p.split = B;
+    p.permC = 0; p.permP = 0;
+    rc = (dtype == BVAE_F32) ? wide_f_launch<float, float>(p, st) : wide_f_launch<__nv_bfloat16, __nv_bfloat16>(p, st);
+    if (rc != BVAE_OK) return rc;
+  }
+  {  // dW[n][g(f')] = sum_b D[b][n] * h[b][f']
+    FcWide p;
+    p.A = w.D; p.a_sm = 1; p.a_sk = 2 * L; p.M = 2 * L; p.K = B; p.ones_row = -1; p.a_clamp = 0.f;
+    p.Bm = h; p.F = F; p.bias = nullptr;
+    p.out0 = dw_mu; p.o0_sm = F; p.o0_sf = 1; p.out1 = dw_logvar; p.o1_sm = F; p.o1_sf = 1; p.split = L;
+    p.permC = C; p.permP = P;
+    rc = (dtype == BVAE_F32) ? wide_f_launch<float, float>(p, st) : wide_f_launch<__nv_bfloat16, float>(p, st);
+    if (rc != BVAE_OK) return rc;
+  }
+  heads_db_kernel<<<cdiv(2 * L, 128), 128, 0, st>>>(w.D, db_mu, db_logvar, B, L);
+  BVAE_LAUNCH_CHECK("heads_db");
+  return BVAE_OK;
+}
+
+extern "C" size_t bvae_fc_dec_workspace(int B, int L, int F) {
+  if (B <= 0 || L <= 0 || F <= 0) return 0;
+  return fcdec_ws_carve(nullptr, B, L, F).bytes;
+}
+
+extern "C" int bvae_fc_dec_fwd(const float* z, const void* wd, const float* bd, void* h0, float z_clamp, int B, int L,
+                               int F, int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(z && wd && bd && h0, BVAE_ERR_ARG, "fc_dec_fwd: null pointer");
+  BVAE_REQUIRE(B > 0 && L > 0 && F > 0, BVAE_ERR_ARG, "fc_dec_fwd: empty shape");
+  BVAE_REQUIRE(dtype == BVAE_F32 || dtype == BVAE_BF16, BVAE_ERR_UNSUPPORTED, "fc_dec_fwd: dtype %d", dtype);
+  cudaStream_t st = as_stream(stream);
+  FcWide p;
+  p.A = z; p.a_sm = L; p.a_sk = 1; p.M = B; p.K = L; p.ones_row = -1; p.a_clamp = z_clamp;
+  p.Bm = wd; p.F = F; p.bias = bd;
+  p.out0 = h0; p.o0_sm = F; p.o0_sf = 1; p.out1 = h0; p.o1_sm = F; p.o1_sf = 1; p.split = B;
+  p.permC = 0; p.permP = 0;
+  return (dtype == BVAE_F32) ? wide_f_launch<float, float>(p, st) : wide_f_launch<__nv_bfloat16, __nv_bfloat16>(p, st);
+}
+
+extern "C" int bvae_fc_dec_bwd(const void* dh0, const float* z, const void* wd, float z_clamp, float* dz, float* dw,
+                               float* db, void* ws, size_t ws_bytes, int B, int L, int C, int P, int dtype,
+                               bvae_stream_t stream) {
+  BVAE_REQUIRE(dh0 && z && wd && dz && dw && db && ws, BVAE_ERR_ARG, "fc_dec_bwd: null pointer");
+  BVAE_REQUIRE(B > 0 && L > 0 && C > 0 && P > 0, BVAE_ERR_ARG, "fc_dec_bwd: empty shape");
+  const int F = C * P;
+  BVAE_REQUIRE(ws_bytes >= bvae_fc_dec_workspace(B, L, F), BVAE_ERR_WORKSPACE, "fc_dec_bwd: workspace too small");
+  BVAE_REQUIRE(dtype == BVAE_F32 || dtype == BVAE_BF16, BVAE_ERR_UNSUPPORTED, "fc_dec_bwd: dtype %d", dtype);
+  cudaStream_t st = as_stream(stream);
+  FcDecWs w = fcdec_ws_carve(ws, B, L, F);
+  // dz = dh0 . wd^T (reduce over F), then mask by the latent clamp
+  int rc = (dtype == BVAE_F32) ? reduce_f_launch<float>(dh0, wd, w.part, B, L, F, st)
+                               : reduce_f_launch<__nv_bfloat16>(dh0, wd, w.part, B, L, F, st);
+  if (rc != BVAE_OK) return rc;
+  const int n = B * L;
+  fcdec_dz_kernel<<<cdiv(n, 256), 256, 0, st>>>(w.part, cdiv(F, RF_CHUNK), z, z_clamp, dz, n);
+  BVAE_LAUNCH_CHECK("fcdec_dz");
+  // dW[g(f')][l] = sum_b zc[b][l] * dh0[b][f'];  db[g(f')] = sum_b dh0[b][f']  (ones row l == L)
+  FcWide p;
+  p.A = z; p.a_sm = 1; p.a_sk = L; p.M = L + 1; p.K = B; p.ones_row = L; p.a_clamp = z_clamp;
+  p.Bm = dh0; p.F = F; p.bias = nullptr;
+  p.out0 = dw; p.o0_sm = 1; p.o0_sf = L; p.out1 = db; p.o1_sm = 0; p.o1_sf = 1; p.split = L;
+  p.permC = C; p.permP = P;
+  return (dtype == BVAE_F32) ? wide_f_launch<float, float>(p, st) : wide_f_launch<__nv_bfloat16, float>(p, st);
+}

@@ -1,0 +1,616 @@
+// GroupNorm(1,C) + ReLU + Squeeze-and-Excitation, fused forward / backward (memory bound).
+//
+// Replaces native_group_norm + relu_ + adaptive_avg_pool2d + 2x linear + sigmoid + mul
+// (reference: src/models/beta_vae.py:41-46, 61-66; src/models/se_blocks.py:15-19) and their
+// autograd backward.
+//
+// Data layout: y/out/dout/dy are [B][P][C] (NHWC, P = H*W).  One CTA owns a contiguous run
+// of pixels of one sample ("chunk"); thread t owns one 16-byte channel vector (column
+// t % CV) and walks pixel rows t / CV, +R, +2R ... so every warp-level access is a run of
+// consecutive 16-byte vectors.  Per-(sample, channel) sums leave the CTA as fp32 partials
+// [B][chunk][C] and are combined by the tiny per-sample kernel that also does the SE
+// mat-vecs with warp shuffles; no atomics, so results are run-to-run deterministic.
+//
+// Forward  : stats pass (read y) -> pool pass (read y) -> excite (tiny) -> scale pass (read y, write out)
+// Backward : reduce pass (read dout,y) -> mid (tiny, per sample) -> params (tiny) -> apply pass (read dout,y, write dy)
+#include "common.cuh"
+
+namespace bvae {
+
+static constexpr int kGnThreads = 256;
+static constexpr float kGnEps = 1e-5f;  // nn.GroupNorm default
+
+struct GnGeom {
+  int cv;       // 16-byte vectors per pixel
+  int rows;     // pixel rows walked in parallel by one CTA
+  int threads;  // cv * rows
+  int pc;       // pixels per chunk
+  int nchunks;
+};
+
+static inline int gn_pixels_per_chunk(int P, int C) {
+  int pc = 16384 / (C > 0 ? C : 1);
+  if (pc < 8) pc = 8;
+  if (pc > P) pc = P;
+  return pc;
+}
+static inline int gn_num_chunks(int P, int C) { return cdiv(P, gn_pixels_per_chunk(P, C)); }
+
+static inline bool gn_geom(int P, int C, int vec, GnGeom* g) {
+  if (C % vec != 0) return false;
+  g->cv = C / vec;
+  if (g->cv > kGnThreads) return false;
+  g->rows = kGnThreads / g->cv;
+  if (g->rows < 1) g->rows = 1;
+  g->threads = g->cv * g->rows;
+  g->pc = gn_pixels_per_chunk(P, C);
+  g->nchunks = cdiv(P, g->pc);
+  return true;
+}
+
+// Every CTA re-derives (mean, rstd) of its sample from the stats partials: nchunks doubles.
+__device__ __forceinline__ void sample_stats(const double* __restrict__ part, int nchunks, double count,
+                                             float* mean_out, float* rstd_out, double* red) {
+  double s = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < nchunks; i += blockDim.x) {
+    s += part[2 * i];
+    ss += part[2 * i + 1];
+  }
+  s = block_sum(s, red);
+  ss = block_sum(ss, red);
+  const double mean = s / count;
+  double var = ss / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  *mean_out = (float)mean;
+  *rstd_out = (float)(1.0 / sqrt(var + (double)kGnEps));
+}
+
+// ------------------------------------------------------------------ forward: statistics
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restrict__ y, double* __restrict__ part,
+                                                              int P, int C, int cv, int rows, int pc) {
+  __shared__ double red[32];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const int p0 = chunk * pc, p1 = min(P, p0 + pc);
+  const T* base = y + ((size_t)b * P) * C + (size_t)col * Vec16<T>::N;
+  float s = 0.f, ss = 0.f;
+#pragma unroll 4
+  for (int p = p0 + row; p < p1; p += rows) {
+    Vec16<T> v;
+    v.load(base + (size_t)p * C);
+#pragma unroll
+    for (int i = 0; i < Vec16<T>::N; ++i) {
+      s += v.v[i];
+      ss = fmaf(v.v[i], v.v[i], ss);
+    }
+  }
+  double ds = block_sum((double)s, red);
+  double dss = block_sum((double)ss, red);
+  if (threadIdx.x == 0) {
+    double* o = part + ((size_t)b * gridDim.x + chunk) * 2;
+    o[0] = ds;
+    o[1] = dss;
+  }
+}
+
+// ------------------------------------------------------------------ forward: pooled sums over positive pixels
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads)
+    gn_pool_kernel(const T* __restrict__ y, const double* __restrict__ spart, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ cpart, float* __restrict__ xpart,
+                   float* __restrict__ stats, int P, int C, int cv, int rows, int pc) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];  // [rows][cv*V] x 2
+  __shared__ double red[32];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  float mean, rstd;
+  sample_stats(spart + (size_t)b * nchunks * 2, nchunks, (double)P * C, &mean, &rstd, red);
+  if (chunk == 0 && threadIdx.x == 0) {
+    stats[2 * b] = mean;
+    stats[2 * b + 1] = rstd;
+  }
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const int p0 = chunk * pc, p1 = min(P, p0 + pc);
+  float g[V], bt[V], cnt[V], sx[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = gamma[col * V + i];
+    bt[i] = beta[col * V + i];
+    cnt[i] = 0.f;
+    sx[i] = 0.f;
+  }
+  const T* base = y + ((size_t)b * P) * C + (size_t)col * V;
+#pragma unroll 4
+  for (int p = p0 + row; p < p1; p += rows) {
+    Vec16<T> v;
+    v.load(base + (size_t)p * C);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xh = (v.v[i] - mean) * rstd;
+      const bool pos = fmaf(xh, g[i], bt[i]) > 0.f;
+      cnt[i] += pos ? 1.f : 0.f;
+      sx[i] += pos ? xh : 0.f;
+    }
+  }
+  float* s0 = sm;
+  float* s1 = sm + rows * C;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    s0[row * C + col * V + i] = cnt[i];
+    s1[row * C + col * V + i] = sx[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      a += s0[r * C + c];
+      q += s1[r * C + c];
+    }
+    const size_t o = ((size_t)b * nchunks + chunk) * C + c;
+    cpart[o] = a;
+    xpart[o] = q;
+  }
+}
+
+// ------------------------------------------------------------------ forward: excitation (one CTA per sample)
+__global__ void __launch_bounds__(256)
+    se_excite_kernel(const float* __restrict__ cpart, const float* __restrict__ xpart, int nchunks,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ w1,
+                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                     float* __restrict__ cpos, float* __restrict__ spos, float* __restrict__ hidden,
+                     float* __restrict__ gate, int P, int C, int R) {
+  extern __shared__ float sm[];  // pool[C] + hid[R]
+  float* pool = sm;
+  float* hid = sm + C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      const size_t o = ((size_t)b * nchunks + k) * C + c;
+      a += cpart[o];
+      q += xpart[o];
+    }
+    cpos[(size_t)b * C + c] = a;
+    spos[(size_t)b * C + c] = q;
+    pool[c] = (gamma[c] * q + beta[c] * a) / (float)P;  // mean over pixels of relu(gn(y))
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int j = warp; j < R; j += nwarp) {  // warp-shuffle mat-vec: hidden = relu(W1 pool + b1)
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], pool[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float h = fmaxf(acc + b1[j], 0.f);
+      hid[j] = h;
+      hidden[(size_t)b * R + j] = h;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // gate = sigmoid(W2 hidden + b2)
+    float acc = b2[c];
+    for (int j = 0; j < R; ++j) acc = fmaf(w2[(size_t)c * R + j], hid[j], acc);
+    gate[(size_t)b * C + c] = 1.0f / (1.0f + expf(-acc));
+  }
+}
+
+// ------------------------------------------------------------------ forward: normalise + relu + rescale
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads)
+    gn_scale_kernel(const T* __restrict__ y, T* __restrict__ out, const double* __restrict__ spart,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ gate,
+                    float* __restrict__ stats, int P, int C, int cv, int rows, int pc) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ double red[32];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  float mean, rstd;
+  sample_stats(spart + (size_t)b * nchunks * 2, nchunks, (double)P * C, &mean, &rstd, red);
+  if (chunk == 0 && threadIdx.x == 0) {
+    stats[2 * b] = mean;
+    stats[2 * b + 1] = rstd;
+  }
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const int p0 = chunk * pc, p1 = min(P, p0 + pc);
+  float g[V], bt[V], sc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = gamma[col * V + i];
+    bt[i] = beta[col * V + i];
+    sc[i] = gate ? gate[(size_t)b * C + col * V + i] : 1.f;
+  }
+  const size_t off = ((size_t)b * P) * C + (size_t)col * V;
+#pragma unroll 4
+  for (int p = p0 + row; p < p1; p += rows) {
+    Vec16<T> v;
+    v.load(y + off + (size_t)p * C);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      // same expression as the pool/backward passes so the >0 mask is identical everywhere
+      const float xh = (v.v[i] - mean) * rstd;
+      v.v[i] = fmaxf(fmaf(xh, g[i], bt[i]), 0.f) * sc[i];
+    }
+    v.store(out + off + (size_t)p * C);
+  }
+}
+
+// ------------------------------------------------------------------ backward: per-(sample,channel) reductions
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads)
+    gn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ y, const float* __restrict__ stats,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ a1part, float* __restrict__ a2part, int P, int C, int cv, int rows,
+                         int pc) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const int p0 = chunk * pc, p1 = min(P, p0 + pc);
+  float g[V], bt[V], a1[V], a2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = gamma[col * V + i];
+    bt[i] = beta[col * V + i];
+    a1[i] = 0.f;
+    a2[i] = 0.f;
+  }
+  const size_t off = ((size_t)b * P) * C + (size_t)col * V;
+#pragma unroll 2
+  for (int p = p0 + row; p < p1; p += rows) {
+    Vec16<T> v, d;
+    v.load(y + off + (size_t)p * C);
+    d.load(dout + off + (size_t)p * C);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xh = (v.v[i] - mean) * rstd;
+      const float dm = (fmaf(xh, g[i], bt[i]) > 0.f) ? d.v[i] : 0.f;
+      a1[i] += dm;
+      a2[i] = fmaf(dm, xh, a2[i]);
+    }
+  }
+  float* s0 = sm;
+  float* s1 = sm + rows * C;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    s0[row * C + col * V + i] = a1[i];
+    s1[row * C + col * V + i] = a2[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      a += s0[r * C + c];
+      q += s1[r * C + c];
+    }
+    const size_t o = ((size_t)b * nchunks + chunk) * C + c;
+    a1part[o] = a;
+    a2part[o] = q;
+  }
+}
+
+// ------------------------------------------------------------------ backward: per-sample SE + GN coefficients
+// Per sample b (one CTA):  A1[c] = sum_p dout*m, A2[c] = sum_p dout*m*xhat  (m = relu mask)
+//   ds      = gamma*A2 + beta*A1                     (d gate, since a = relu(gamma*xhat+beta))
+//   dz2     = ds * s(1-s);  dh = W2^T dz2;  dz1 = dh * (hidden>0);  dpool = W1^T dz1
+//   G1      = s*A1 + dpool/P * cpos    (= sum_p g,       g = d relu-input)
+//   G2      = s*A2 + dpool/P * spos    (= sum_p g*xhat)
+//   S1, S2  = sum_c gamma*G1, sum_c gamma*G2          (GroupNorm backward sums)
+__global__ void __launch_bounds__(256)
+    gn_bwd_mid_kernel(const float* __restrict__ a1part, const float* __restrict__ a2part, int nchunks,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ w1,
+                      const float* __restrict__ w2, const float* __restrict__ cpos, const float* __restrict__ spos,
+                      const float* __restrict__ hidden, const float* __restrict__ gate, float* __restrict__ G1o,
+                      float* __restrict__ G2o, float* __restrict__ dz2o, float* __restrict__ dz1o,
+                      float* __restrict__ dpoolo, float* __restrict__ coef, int P, int C, int R) {
+  extern __shared__ float sm[];  // A1[C] A2[C] dz2[C] dz1[R]
+  __shared__ float red[32];
+  float* A1 = sm;
+  float* A2 = sm + C;
+  float* dz2 = sm + 2 * C;
+  float* dz1 = sm + 3 * C;
+  const int b = blockIdx.x;
+  const bool has_se = (w1 != nullptr);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      const size_t o = ((size_t)b * nchunks + k) * C + c;
+      a += a1part[o];
+      q += a2part[o];
+    }
+    A1[c] = a;
+    A2[c] = q;
+    if (has_se) {
+      const float s = gate[(size_t)b * C + c];
+      const float ds = gamma[c] * q + beta[c] * a;
+      const float t = ds * s * (1.f - s);
+      dz2[c] = t;
+      dz2o[(size_t)b * C + c] = t;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (has_se) {
+    for (int j = warp; j < R; j += nwarp) {  // dh[j] = sum_c dz2[c] * W2[c][j]
+      float acc = 0.f;
+      for (int c = lane; c < C; c += 32) acc = fmaf(dz2[c], w2[(size_t)c * R + j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float t = hidden[(size_t)b * R + j] > 0.f ? acc : 0.f;
+        dz1[j] = t;
+        dz1o[(size_t)b * R + j] = t;
+      }
+    }
+    __syncthreads();
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g1, g2;
+    if (has_se) {
+      float dp = 0.f;
+      for (int j = 0; j < R; ++j) dp = fmaf(dz1[j], w1[(size_t)j * C + c], dp);
+      dp /= (float)P;
+      dpoolo[(size_t)b * C + c] = dp;
+      const float s = gate[(size_t)b * C + c];
+      g1 = fmaf(dp, cpos[(size_t)b * C + c], s * A1[c]);
+      g2 = fmaf(dp, spos[(size_t)b * C + c], s * A2[c]);
+    } else {
+      g1 = A1[c];
+      g2 = A2[c];
+    }
+    G1o[(size_t)b * C + c] = g1;
+    G2o[(size_t)b * C + c] = g2;
+    s1 = fmaf(gamma[c], g1, s1);
+    s2 = fmaf(gamma[c], g2, s2);
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    coef[2 * b] = s1;
+    coef[2 * b + 1] = s2;
+  }
+}
+
+// ------------------------------------------------------------------ backward: parameter gradients (sum over batch)
+__global__ void __launch_bounds__(256)
+    gn_bwd_params_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
+                         const float* __restrict__ dz1, const float* __restrict__ cpos,
+                         const float* __restrict__ spos, const float* __restrict__ hidden,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
+                         float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int has_se) {
+  // job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R]
+  const long long n_gb = C, n_w2 = has_se ? (long long)C * R : 0, n_w1 = n_w2, n_b1 = has_se ? R : 0;
+  const long long total = n_gb + n_w2 + n_w1 + n_b1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_gb) {
+      const int c = (int)i;
+      float dg = 0.f, db = 0.f, d2 = 0.f;
+      for (int b = 0; b < B; ++b) {
+        dg += G2[(size_t)b * C + c];
+        db += G1[(size_t)b * C + c];
+        if (has_se) d2 += dz2[(size_t)b * C + c];
+      }
+      dgamma[c] = dg;
+      dbeta[c] = db;
+      if (has_se) db2[c] = d2;
+    } else if (i < n_gb + n_w2) {
+      const long long k = i - n_gb;
+      const int c = (int)(k / R), j = (int)(k % R);
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc = fmaf(dz2[(size_t)b * C + c], hidden[(size_t)b * R + j], acc);
+      dw2[k] = acc;
+    } else if (i < n_gb + n_w2 + n_w1) {
+      const long long k = i - n_gb - n_w2;
+      const int j = (int)(k / C), c = (int)(k % C);
+      float acc = 0.f;
+      const float gc = gamma[c], bc = beta[c];
+      for (int b = 0; b < B; ++b) {
+        const float pool = (gc * spos[(size_t)b * C + c] + bc * cpos[(size_t)b * C + c]) / (float)P;
+        acc = fmaf(dz1[(size_t)b * R + j], pool, acc);
+      }
+      dw1[k] = acc;
+    } else {
+      const int j = (int)(i - n_gb - n_w2 - n_w1);
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += dz1[(size_t)b * R + j];
+      db1[j] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward: write dy
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads)
+    gn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ y, T* __restrict__ dy,
+                        const float* __restrict__ stats, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ gate,
+                        const float* __restrict__ dpool, const float* __restrict__ coef, int P, int C, int cv,
+                        int rows, int pc) {
+  constexpr int V = Vec16<T>::N;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+  const float invM = 1.0f / ((float)P * (float)C);
+  const float S1 = coef[2 * b] * invM, S2 = coef[2 * b + 1] * invM;
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const int p0 = chunk * pc, p1 = min(P, p0 + pc);
+  float g[V], bt[V], sc[V], dp[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = gamma[col * V + i];
+    bt[i] = beta[col * V + i];
+    sc[i] = gate ? gate[(size_t)b * C + col * V + i] : 1.f;
+    dp[i] = gate ? dpool[(size_t)b * C + col * V + i] : 0.f;
+  }
+  const size_t off = ((size_t)b * P) * C + (size_t)col * V;
+#pragma unroll 2
+  for (int p = p0 + row; p < p1; p += rows) {
+    Vec16<T> v, d;
+    v.load(y + off + (size_t)p * C);
+    d.load(dout + off + (size_t)p * C);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xh = (v.v[i] - mean) * rstd;
+      const float gg = (fmaf(xh, g[i], bt[i]) > 0.f) ? fmaf(d.v[i], sc[i], dp[i]) : 0.f;
+      // dy = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat))
+      d.v[i] = rstd * (fmaf(gg, g[i], -S1) - xh * S2);
+    }
+    d.store(dy + off + (size_t)p * C);
+  }
+}
+
+// ------------------------------------------------------------------ workspace layout
+struct GnWs {
+  double* spart;  // [B][nchunks][2]
+  float* p0;      // [B][nchunks][C]
+  float* p1;      // [B][nchunks][C]
+  float* G1;      // [B][C]
+  float* G2;      // [B][C]
+  float* dz2;     // [B][C]
+  float* dpool;   // [B][C]
+  float* dz1;     // [B][Rmax=C]
+  float* coef;    // [B][2]
+  size_t bytes;
+};
+
+static GnWs gn_ws_carve(void* base, int B, int P, int C) {
+  const int nch = gn_num_chunks(P, C);
+  GnWs w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  w.spart = reinterpret_cast<double*>(take((size_t)B * nch * 2 * sizeof(double)));
+  w.p0 = reinterpret_cast<float*>(take((size_t)B * nch * C * sizeof(float)));
+  w.p1 = reinterpret_cast<float*>(take((size_t)B * nch * C * sizeof(float)));
+  w.G1 = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
+  w.G2 = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
+  w.dz2 = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
+  w.dpool = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
+  w.dz1 = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
+  w.coef = reinterpret_cast<float*>(take((size_t)B * 2 * sizeof(float)));
+  w.bytes = off;
+  return w;
+}
+
+template <typename T>
+static int gn_fwd_impl(const T* y, T* out, const float* gamma, const float* beta, const float* w1, const float* b1,
+                       const float* w2, const float* b2, int B, int P, int C, int R, float* stats, float* cpos,
+                       float* spos, float* hidden, float* gate, void* ws, cudaStream_t st) {
+  GnGeom g;
+  BVAE_REQUIRE(gn_geom(P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
+               "gn_relu_se: C=%d must be a multiple of %d with C/%d <= 256", C, Vec16<T>::N, Vec16<T>::N);
+  GnWs w = gn_ws_carve(ws, B, P, C);
+  dim3 grid(g.nchunks, B);
+  gn_stats_kernel<T><<<grid, g.threads, 0, st>>>(y, w.spart, P, C, g.cv, g.rows, g.pc);
+  BVAE_LAUNCH_CHECK("gn_stats");
+  const bool has_se = w1 != nullptr;
+  if (has_se) {
+    const size_t sm = (size_t)2 * g.rows * C * sizeof(float);
+    gn_pool_kernel<T><<<grid, g.threads, sm, st>>>(y, w.spart, gamma, beta, w.p0, w.p1, stats, P, C, g.cv, g.rows,
+                                                   g.pc);
+    BVAE_LAUNCH_CHECK("gn_pool");
+    se_excite_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(w.p0, w.p1, g.nchunks, gamma, beta, w1, b1, w2,
+                                                                      b2, cpos, spos, hidden, gate, P, C, R);
+    BVAE_LAUNCH_CHECK("se_excite");
+  }
+  gn_scale_kernel<T><<<grid, g.threads, 0, st>>>(y, out, w.spart, gamma, beta, has_se ? gate : nullptr, stats, P, C,
+                                                 g.cv, g.rows, g.pc);
+  BVAE_LAUNCH_CHECK("gn_scale");
+  return BVAE_OK;
+}
+
+template <typename T>
+static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, const float* beta, const float* w1,
+                       const float* w2, int B, int P, int C, int R, const float* stats, const float* cpos,
+                       const float* spos, const float* hidden, const float* gate, float* dgamma, float* dbeta,
+                       float* dw1, float* db1, float* dw2, float* db2, void* ws, cudaStream_t st) {
+  GnGeom g;
+  BVAE_REQUIRE(gn_geom(P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
+               "gn_relu_se: C=%d must be a multiple of %d with C/%d <= 256", C, Vec16<T>::N, Vec16<T>::N);
+  GnWs w = gn_ws_carve(ws, B, P, C);
+  const bool has_se = w1 != nullptr;
+  dim3 grid(g.nchunks, B);
+  const size_t sm = (size_t)2 * g.rows * C * sizeof(float);
+  gn_bwd_reduce_kernel<T><<<grid, g.threads, sm, st>>>(dout, y, stats, gamma, beta, w.p0, w.p1, P, C, g.cv, g.rows,
+                                                       g.pc);
+  BVAE_LAUNCH_CHECK("gn_bwd_reduce");
+  gn_bwd_mid_kernel<<<B, 256, (size_t)(3 * C + (has_se ? R : 0)) * sizeof(float), st>>>(
+      w.p0, w.p1, g.nchunks, gamma, beta, w1, w2, cpos, spos, hidden, gate, w.G1, w.G2, w.dz2, w.dz1, w.dpool, w.coef,
+      P, C, R);
+  BVAE_LAUNCH_CHECK("gn_bwd_mid");
+  const long long jobs = (long long)C + (has_se ? 2LL * C * R + R : 0);
+  int pblocks = (int)((jobs + 255) / 256);
+  if (pblocks > 4 * num_sms()) pblocks = 4 * num_sms();
+  gn_bwd_params_kernel<<<pblocks, 256, 0, st>>>(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma,
+                                                dbeta, dw1, db1, dw2, db2, B, P, C, R, has_se ? 1 : 0);
+  BVAE_LAUNCH_CHECK("gn_bwd_params");
+  gn_bwd_apply_kernel<T><<<grid, g.threads, 0, st>>>(dout, y, dy, stats, gamma, beta, has_se ? gate : nullptr,
+                                                     w.dpool, w.coef, P, C, g.cv, g.rows, g.pc);
+  BVAE_LAUNCH_CHECK("gn_bwd_apply");
+  return BVAE_OK;
+}
+
+}  // namespace bvae
+
+using namespace bvae;
+
+extern "C" size_t bvae_gn_relu_se_workspace(int B, int P, int C) {
+  if (B <= 0 || P <= 0 || C <= 0) return 0;
+  return gn_ws_carve(nullptr, B, P, C).bytes;
+}
+
+extern "C" int bvae_gn_relu_se_fwd(const void* y, void* out, const float* gamma, const float* beta, const float* w1,
+                                   const float* b1, const float* w2, const float* b2, int B, int P, int C, int R,
+                                   float* stats, float* cpos, float* spos, float* hidden, float* gate, void* ws,
+                                   size_t ws_bytes, int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(y && out && gamma && beta && stats && ws, BVAE_ERR_ARG, "gn_relu_se_fwd: null pointer");
+  BVAE_REQUIRE(B > 0 && P > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_fwd: empty shape B=%d P=%d C=%d", B, P, C);
+  if (w1) {
+    BVAE_REQUIRE(b1 && w2 && b2 && cpos && spos && hidden && gate && R > 0, BVAE_ERR_ARG,
+                 "gn_relu_se_fwd: SE requested but SE buffers missing");
+    BVAE_REQUIRE((size_t)(C + R) * 4 <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "gn_relu_se: C+R too large");
+  }
+  BVAE_REQUIRE(ws_bytes >= bvae_gn_relu_se_workspace(B, P, C), BVAE_ERR_WORKSPACE, "gn_relu_se_fwd: workspace %zu < %zu",
+               ws_bytes, bvae_gn_relu_se_workspace(B, P, C));
+  cudaStream_t st = as_stream(stream);
+  if (dtype == BVAE_F32)
+    return gn_fwd_impl<float>((const float*)y, (float*)out, gamma, beta, w1, b1, w2, b2, B, P, C, R, stats, cpos,
+                              spos, hidden, gate, ws, st);
+  if (dtype == BVAE_BF16)
+    return gn_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)y, (__nv_bfloat16*)out, gamma, beta, w1, b1, w2, b2, B, P,
+                                      C, R, stats, cpos, spos, hidden, gate, ws, st);
+  BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "gn_relu_se_fwd: dtype %d", dtype);
+}
+
+extern "C" int bvae_gn_relu_se_bwd(const void* dout, const void* y, void* dy, const float* gamma, const float* beta,
+                                   const float* w1, const float* b1, const float* w2, const float* b2, int B, int P,
+                                   int C, int R, const float* stats, const float* cpos, const float* spos,
+                                   const float* hidden, const float* gate, float* dgamma, float* dbeta, float* dw1,
+                                   float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
+                                   bvae_stream_t stream) {
+  (void)b1;
+  (void)b2;
+  BVAE_REQUIRE(dout && y && dy && gamma && beta && stats && dgamma && dbeta && ws, BVAE_ERR_ARG,
+               "gn_relu_se_bwd: null pointer");
+  BVAE_REQUIRE(B > 0 && P > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_bwd: empty shape");
+  if (w1) {
+    BVAE_REQUIRE(w2 && cpos && spos && hidden && gate && dw1 && db1 && dw2 && db2 && R > 0, BVAE_ERR_ARG,
+                 "gn_relu_se_bwd: SE requested but SE buffers missing");
+    BVAE_REQUIRE((size_t)(3 * C + R) * 4 <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "gn_relu_se: C too large");
+  }
+  BVAE_REQUIRE(ws_bytes >= bvae_gn_relu_se_workspace(B, P, C), BVAE_ERR_WORKSPACE, "gn_relu_se_bwd: workspace small");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == BVAE_F32)
+    return gn_bwd_impl<float>((const float*)dout, (const float*)y, (float*)dy, gamma, beta, w1, w2, B, P, C, R, stats,
+                              cpos, spos, hidden, gate, dgamma, dbeta, dw1, db1, dw2, db2, ws, st);
+  if (dtype == BVAE_BF16)
+    return gn_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, gamma,
+                                      beta, w1, w2, B, P, C, R, stats, cpos, spos, hidden, gate, dgamma, dbeta, dw1,
+                                      db1, dw2, db2, ws, st);
+  BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "gn_relu_se_bwd: dtype %d", dtype);
+}
