@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the Beta-VAE-SE training hot path on B200 (BASELINE.json metric:
+train images/sec, fwd+bwd, at 1/2/4/8 GPUs, with the reference's CPU path timed beside it).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W  # the reference's CPU path (oracle port)
+
+A "step" is one full training step of the path on one batch: zero_grad, BetaVAE.loss() under
+bf16 autocast (capacity objective C=30, gamma=1, focal-frequency term 0.5 -- the shipped default
+config's first-epoch settings), backward, gradient all-reduce (N>1), global-norm clip 3.0 and
+Adam.  Workload = beta-vae_b200/configs/beta_vae_se.yaml (128x128 grayscale, base 64, 4 blocks,
+latent 64), per-GPU batch = training.batch_size (32), synthetic 4-class MRI-shaped slices,
+random-init (Kaiming) weights.  Weak scaling: per-GPU batch fixed.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "beta-vae_b200")
+for p in (ROOT, os.path.join(PKG, "src"), PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+CONFIG = os.path.join(PKG, "configs", "beta_vae_se.yaml")
+METRIC = "train images/sec (fwd+bwd)"
+LOSS_KW = dict(beta=1.0, capacity=30.0, free_bits=0.0, capacity_weight=1.0)
+
+
+def weight_init(m):
+    # what the reference's train loop applies (src/training/train.py:217-221)
+    if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d, torch.nn.Linear)):
+        torch.nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+        if m.bias is not None:
+            torch.nn.init.zeros_(m.bias)
+
+
+def load_cfg():
+    with open(CONFIG) as f:
+        return yaml.safe_load(f)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port; /root/reference
+# does not exist on the GPU box).  Also used, on a bounded sample, for `cpu_baseline`.
+# ----------------------------------------------------------------------------------------------
+def run_cpu_reference(cfg, batch, steps, warmup):
+    from types import SimpleNamespace
+
+    from oracle import beta_vae_oracle as O
+
+    def ns(d):
+        return SimpleNamespace(**{k: ns(v) for k, v in d.items()}) if isinstance(d, dict) else d
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    spec = O.spec_from_config(ns(cfg))
+    sd = {k: v.requires_grad_(True) for k, v in O.init_params(spec, cfg["data"]["seed"]).items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=cfg["optimization"]["lr"])
+    xs = [O.synthetic_batch(batch, spec.image_size, seed=s) for s in range(2)]
+    g = torch.Generator().manual_seed(1)
+    times = []
+    for i in range(warmup + steps):
+        eps = torch.randn(batch, spec.latent_dim, generator=g)
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = O.loss(sd, spec, xs[i % 2], eps, **LOSS_KW)
+        out["total"].backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), cfg["training"]["grad_clip"])
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec * 1e3, threads
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = load_cfg()
+    batch = cfg["training"]["batch_size"]
+    ips, ms, threads = run_cpu_reference(cfg, batch, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs/beta_vae_se.yaml default Beta-VAE-SE training step "
+                               "(loss+backward+clip+Adam), CPU fp32, batch 32", "batch_per_step": batch},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full train steps at batch {batch} (oracle port of the reference "
+                                   f"path, torch CPU fp32, {threads} threads)"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clock sampling during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------------
+def cuda_main(args):
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+
+    from bvae_rt import lib, profiler
+    from bvae_rt.data import synthetic_batch
+    from bvae_rt.engine import TrainEngine
+    from models.beta_vae import BetaVAE
+    from utils.brain_tumor_utils.config_parser import freeze
+    lib.load()
+    assert lib.query("bvae_device_ok") == 1, "not a compute-capability-10.x device"
+
+    cfg = load_cfg()
+    batch = args.batch or cfg["training"]["batch_size"]
+    size, latent = cfg["data"]["image_size"], cfg["model"]["latent_dim"]
+    torch.manual_seed(cfg["data"]["seed"])
+    model = BetaVAE(freeze(cfg))
+    model.apply(weight_init)
+    model = model.to(dev).train()
+    engine = TrainEngine(model, lr=cfg["optimization"]["lr"], clip=cfg["training"]["grad_clip"])
+
+    n_batches = 8  # rotate distinct device-resident batches so inputs are never L2-warm
+    xs = [synthetic_batch(batch, size, seed=1000 * rank + i, device=dev) for i in range(n_batches)]
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    scal = torch.zeros(4, device=dev)
+
+    def train_step(x):
+        engine.zero_grad()
+        eps = torch.randn(batch, latent, device=dev, generator=gen)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model.loss(x, eps=eps, **LOSS_KW)
+        out["total"].backward()
+        engine.step()
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        sync_all()
+        return ms
+
+    warm = max(3, args.warmup)
+    for i in range(warm):
+        train_step(xs[i % n_batches])
+    # ---- (1) device-resident throughput
+    l0 = lib.query("bvae_launch_count")
+    with ClockSampler(local) as clk:
+        ms = timed(lambda i: train_step(xs[i % n_batches]), args.steps)
+    launches = lib.query("bvae_launch_count") - l0
+    value = world * batch * args.steps / (ms / 1e3)
+
+    # ---- (2) end to end through the public API with host buffers
+    host = [x.cpu().pin_memory() for x in xs]
+    xdev = torch.empty_like(xs[0])
+    host_out = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        xdev.copy_(host[i % n_batches], non_blocking=True)           # H2D of this step's input
+        out = train_step(xdev)
+        scal[0], scal[1], scal[2], scal[3] = out["total"].detach(), out["recon"].detach(), out["kl_mean"].detach(), \
+            out["recon_ffl"]
+        host_out.copy_(scal, non_blocking=True)                      # D2H of the step's loss scalars
+        torch.cuda.current_stream().synchronize()                    # the train loop reads them every step
+        return float(host_out[0])
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
+
+    # ---- (3) per-op CUDA-event pass for the roofline of the dominant kernel
+    prof = profiler.start()
+    for i in range(args.steps):
+        train_step(xs[i % n_batches])
+    agg = profiler.stop().summary()
+    peaks = measured_peaks()
+    roofline, top = None, []
+    if agg:
+        total_ms = sum(a["ms"] for a in agg.values())
+        ranked = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        tag, a = ranked[0]
+        per_call_ms = a["ms"] / a["calls"]
+        if tag.startswith("conv_") or tag.startswith("heads") or tag.startswith("fc_dec"):
+            ach = a["flops"] / a["calls"] / (per_call_ms * 1e-3) / 1e12
+            roofline = {"kernel": tag, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + " (sustained bf16)"}
+        else:
+            ach = a["bytes"] / a["calls"] / (per_call_ms * 1e-3) / 1e9
+            roofline = {"kernel": tag, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+        roofline.update({"ms_per_call": per_call_ms, "launches_per_call": a["launches"] / a["calls"],
+                         "share_of_profiled_step": a["ms"] / total_ms})
+        for t, v in ranked[:12]:
+            top.append({"op": t, "ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_ms,
+                        "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else None,
+                        "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else None})
+
+    # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, cms, threads = run_cpu_reference(cfg, batch if batch <= 32 else 32, steps=2, warmup=1)
+        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"2 timed train steps (+1 warm-up) at batch {min(batch, 32)} of the same config: oracle port of "
+                         f"the reference path, torch CPU fp32, {threads} threads, {cms:.0f} ms/step"}
+
+    if rank == 0:
+        act_mb = 2 * 2 * 1998848 * batch * 2 / 1e6  # y + out of every block, bf16, fwd (+ same again in bwd)
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs/beta_vae_se.yaml default Beta-VAE-SE train step "
+                                   "(loss fwd + bwd + grad all-reduce + clip + Adam)",
+                       "image_size": size, "per_gpu_batch": batch, "global_batch": batch * world,
+                       "objective": "capacity C=30 gamma=1, FFL 0.5 (torch.fft), mse",
+                       "parallelism": f"dp{world}",
+                       "l2": f"no explicit flush: a step streams ~{act_mb:.0f} MB of activations plus 8 rotating "
+                             f"input batches, above the 126 MB L2"},
+            "clocks": clk.result(),
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": 16},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "top_ops": top,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: training.batch_size of the config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        cuda_main(args)
+
+
+if __name__ == "__main__":
+    main()

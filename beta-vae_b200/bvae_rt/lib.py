@@ -25,9 +25,9 @@ def _parse_header():
         txt = f.read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     sigs = {}
-    for m in re.finditer(r"(const char\*|size_t|int)\s+(bvae_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+    for m in re.finditer(r"(const char\*|size_t|int|unsigned long long)\s+(bvae_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
         ret, name, params = m.group(1), m.group(2), m.group(3)
-        res = {"const char*": C.c_char_p, "size_t": sz, "int": i32}[ret]
+        res = {"const char*": C.c_char_p, "size_t": sz, "int": i32, "unsigned long long": C.c_ulonglong}[ret]
         args = []
         for prm in [q.strip() for q in params.split(",")]:
             if prm in ("void", ""):

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from . import lib
+from . import lib, profiler
 from .lib import BF16, F32, call, query
 
 
@@ -45,6 +45,45 @@ def code_of(t):
 
 def conv_out(n, stride):
     return (n - 1) // stride + 1
+
+
+class GradArena:
+    """Destination views for parameter gradients (slices of the engine's flat bucket buffers).
+    The backward kernels write straight into them, so a bucket is complete -- and its
+    all-reduce can start -- the moment its last wgrad kernel has been enqueued."""
+
+    def __init__(self):
+        self._views = {}
+
+    def register(self, param, view):
+        self._views[param.data_ptr()] = (param, view)
+
+    def out_for(self, t):
+        ent = self._views.get(t.data_ptr())
+        # only hand out the slot when autograd will *assign* (grad is None); when it is going to
+        # accumulate into an existing .grad the kernel must write somewhere else
+        if ent is not None and ent[0].grad is None and ent[1].shape == t.shape:
+            return ent[1]
+        return None
+
+
+_ARENA = None
+
+
+def set_grad_arena(arena):
+    global _ARENA
+    _ARENA = arena
+
+
+def grad_out(t):
+    """fp32 output tensor for d(loss)/d(t), in the arena when one is installed."""
+    if t is None:
+        return None
+    if _ARENA is not None:
+        v = _ARENA.out_for(t)
+        if v is not None:
+            return v
+    return torch.empty(t.shape, dtype=torch.float32, device=t.device)
 
 
 # --------------------------------------------------------------------------------------
@@ -111,7 +150,10 @@ def nchw_to_nhwc(x, dt):
 def conv3x3_fprop(x, wp, bias, cout, stride, dt):
     B, H, W, Cin = x.shape
     y = torch.empty((B, conv_out(H, stride), conv_out(W, stride), cout), dtype=torch_dtype(dt), device=x.device)
-    call("bvae_conv3x3_fprop", _p(x), _p(wp), _p(bias), _p(y), B, H, W, Cin, cout, stride, code_of(x), dt, _stream())
+    with profiler.region(f"conv_fprop[{H}x{W}x{Cin}->{cout},s{stride}]", flops=2.0 * y.numel() * 9 * Cin,
+                         nbytes=x.numel() * x.element_size() + y.numel() * y.element_size()):
+        call("bvae_conv3x3_fprop", _p(x), _p(wp), _p(bias), _p(y), B, H, W, Cin, cout, stride, code_of(x), dt,
+             _stream())
     return y
 
 
@@ -119,33 +161,41 @@ def conv3x3_dgrad(dy, wpt, in_shape, stride):
     B, H, W, Cin = in_shape
     Cout = dy.shape[3]
     dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
-    call("bvae_conv3x3_dgrad", _p(dy), _p(wpt), _p(dx), B, H, W, Cin, Cout, stride, code_of(dy), _stream())
+    with profiler.region(f"conv_dgrad[{H}x{W}x{Cin}<-{Cout},s{stride}]", flops=2.0 * dy.numel() * 9 * Cin,
+                         nbytes=(dx.numel() + dy.numel()) * dy.element_size()):
+        call("bvae_conv3x3_dgrad", _p(dy), _p(wpt), _p(dx), B, H, W, Cin, Cout, stride, code_of(dy), _stream())
     return dx
 
 
-def conv3x3_wgrad(x, dy, stride, want_bias=True):
+def conv3x3_wgrad(x, dy, stride, want_bias=True, dw=None, db=None):
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
-    dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
-    db = torch.empty((Cout,), dtype=torch.float32, device=x.device) if want_bias else None
+    if dw is None:
+        dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    if db is None and want_bias:
+        db = torch.empty((Cout,), dtype=torch.float32, device=x.device)
     n = query("bvae_conv3x3_wgrad_workspace", B, H, W, Cin, Cout, stride)
     ws = _ws(n, x.device)
-    call("bvae_conv3x3_wgrad", _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), B, H, W, Cin, Cout, stride,
-         code_of(x), code_of(dy), _stream())
+    with profiler.region(f"conv_wgrad[{H}x{W}x{Cin}->{Cout},s{stride}]", flops=2.0 * dy.numel() * 9 * Cin,
+                         nbytes=x.numel() * x.element_size() + dy.numel() * dy.element_size()):
+        call("bvae_conv3x3_wgrad", _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), B, H, W, Cin, Cout, stride,
+             code_of(x), code_of(dy), _stream())
     return dw, db
 
 
 def upsample2x_fwd(x):
     B, H, W, Cc = x.shape
     y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
-    call("bvae_upsample2x_fwd", _p(x), _p(y), B, H, W, Cc, code_of(x), _stream())
+    with profiler.region(f"upsample_fwd[{H}x{W}x{Cc}]", nbytes=(x.numel() + y.numel()) * x.element_size()):
+        call("bvae_upsample2x_fwd", _p(x), _p(y), B, H, W, Cc, code_of(x), _stream())
     return y
 
 
 def upsample2x_bwd(dy):
     B, H2, W2, Cc = dy.shape
     dx = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=dy.dtype, device=dy.device)
-    call("bvae_upsample2x_bwd", _p(dy), _p(dx), B, H2 // 2, W2 // 2, Cc, code_of(dy), _stream())
+    with profiler.region(f"upsample_bwd[{H2 // 2}x{W2 // 2}x{Cc}]", nbytes=(dx.numel() + dy.numel()) * dy.element_size()):
+        call("bvae_upsample2x_bwd", _p(dy), _p(dx), B, H2 // 2, W2 // 2, Cc, code_of(dy), _stream())
     return dx
 
 
@@ -160,8 +210,10 @@ def gn_relu_se_fwd(y, gamma, beta, w1, b1, w2, b2):
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     cpos, spos, hidden, gate = (f(B, Cc), f(B, Cc), f(B, R), f(B, Cc)) if has_se else (None,) * 4
     ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
-    call("bvae_gn_relu_se_fwd", _p(y), _p(out), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P, Cc, R,
-         _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(ws), ws.numel(), code_of(y), _stream())
+    # algorithmic bytes: one read of y + one write of out
+    with profiler.region(f"gn_relu_se_fwd[{H}x{W}x{Cc}]", nbytes=2.0 * y.numel() * y.element_size()):
+        call("bvae_gn_relu_se_fwd", _p(y), _p(out), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P, Cc, R,
+             _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(ws), ws.numel(), code_of(y), _stream())
     return out, (stats, cpos, spos, hidden, gate)
 
 
@@ -173,13 +225,14 @@ def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved):
     has_se = w1 is not None
     R = w1.shape[0] if has_se else 0
     dy = torch.empty_like(y)
-    dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
-    dw1, db1, dw2, db2 = ((torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2))
-                          if has_se else (None,) * 4)
+    dgamma, dbeta = grad_out(gamma), grad_out(beta)
+    dw1, db1, dw2, db2 = (grad_out(w1), grad_out(b1), grad_out(w2), grad_out(b2)) if has_se else (None,) * 4
     ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
-    call("bvae_gn_relu_se_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P,
-         Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1), _p(db1),
-         _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
+    # algorithmic bytes: read dout + read y + write dy
+    with profiler.region(f"gn_relu_se_bwd[{H}x{W}x{Cc}]", nbytes=3.0 * y.numel() * y.element_size()):
+        call("bvae_gn_relu_se_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B,
+             P, Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1), _p(db1),
+             _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
     return dy, dgamma, dbeta, dw1, db1, dw2, db2
 
 
@@ -196,17 +249,17 @@ class ConvGnSeBlock(torch.autograd.Function):
         y = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt)
         out, saved = gn_relu_se_fwd(y, gw, gb, w1, b1, w2, b2)
         stats, cpos, spos, hidden, gate = saved
-        ctx.save_for_backward(xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate)
+        ctx.save_for_backward(xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate, cw, cb)
         ctx.stride, ctx.upsample = stride, upsample
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate = ctx.saved_tensors
+        xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate, cw, cb = ctx.saved_tensors
         dout = dout.contiguous()
         dy, dgw, dgb, dw1, db1, dw2, db2 = gn_relu_se_bwd(dout, y, gw, gb, w1, b1, w2, b2,
                                                           (stats, cpos, spos, hidden, gate))
-        dcw, dcb = conv3x3_wgrad(xin, dy, ctx.stride)
+        dcw, dcb = conv3x3_wgrad(xin, dy, ctx.stride, dw=grad_out(cw), db=grad_out(cb))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = conv3x3_dgrad(dy, wpt, tuple(xin.shape), ctx.stride)
@@ -230,10 +283,12 @@ class HeadsReparamKL(torch.autograd.Function):
         mu, logvar, z, klpd, sc = f(B, L), f(B, L), f(B, L), f(L), f(4)
         lv_pass = torch.empty((B, L), dtype=torch.uint8, device=dev)
         ws = _ws(query("bvae_heads_workspace", B, L, F), dev)
-        call("bvae_heads_reparam_kl_fwd", _p(h), _p(wh), _p(b_mu), _p(b_lv), _p(eps), lo, hi, beta, int(use_cap), cap,
-             cap_w, fb, reg, int(det), _p(mu), _p(logvar), _p(z), _p(klpd), _p(sc), _p(lv_pass), _p(ws), ws.numel(),
-             B, L, F, dt, _stream())
-        ctx.save_for_backward(h, wh, eps, mu, logvar, klpd, sc, lv_pass)
+        with profiler.region("heads_reparam_kl_fwd", flops=4.0 * B * L * F,
+                             nbytes=(h.numel() + wh.numel()) * h.element_size()):
+            call("bvae_heads_reparam_kl_fwd", _p(h), _p(wh), _p(b_mu), _p(b_lv), _p(eps), lo, hi, beta, int(use_cap),
+                 cap, cap_w, fb, reg, int(det), _p(mu), _p(logvar), _p(z), _p(klpd), _p(sc), _p(lv_pass), _p(ws),
+                 ws.numel(), B, L, F, dt, _stream())
+        ctx.save_for_backward(h, wh, eps, mu, logvar, klpd, sc, lv_pass, w_mu, b_mu, w_lv, b_lv)
         ctx.cfg = (beta, int(use_cap), cap, cap_w, fb, reg, int(det), dt, Cc, P, L)
         ctx.mark_non_differentiable(klpd)
         ctx.set_materialize_grads(False)
@@ -241,21 +296,20 @@ class HeadsReparamKL(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_mu, g_lv, g_z, _g_klpd, g_sc):
-        h, wh, eps, mu, logvar, klpd, sc, lv_pass = ctx.saved_tensors
+        h, wh, eps, mu, logvar, klpd, sc, lv_pass, w_mu, b_mu, w_lv, b_lv = ctx.saved_tensors
         beta, use_cap, cap, cap_w, fb, reg, det, dt, Cc, P, L = ctx.cfg
         B = h.shape[0]
         dev = h.device
         c = lambda t: None if t is None else t.contiguous().float()
         g_mu, g_lv, g_z, g_sc = c(g_mu), c(g_lv), c(g_z), c(g_sc)
         dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
-        dwm = torch.empty((L, Cc * P), dtype=torch.float32, device=dev)
-        dwl = torch.empty((L, Cc * P), dtype=torch.float32, device=dev)
-        dbm = torch.empty((L,), dtype=torch.float32, device=dev)
-        dbl = torch.empty((L,), dtype=torch.float32, device=dev)
+        dwm, dwl, dbm, dbl = grad_out(w_mu), grad_out(w_lv), grad_out(b_mu), grad_out(b_lv)
         ws = _ws(query("bvae_heads_workspace", B, L, Cc * P), dev)
-        call("bvae_heads_reparam_kl_bwd", _p(h), _p(wh), _p(eps), _p(mu), _p(logvar), _p(klpd), _p(sc), _p(lv_pass),
-             _p(g_mu), _p(g_lv), _p(g_z), _p(g_sc), beta, use_cap, cap, cap_w, fb, reg, det, _p(dh), _p(dwm), _p(dwl),
-             _p(dbm), _p(dbl), _p(ws), ws.numel(), B, L, Cc, P, dt, _stream())
+        with profiler.region("heads_reparam_kl_bwd", flops=8.0 * B * L * Cc * P,
+                             nbytes=(2 * h.numel() + wh.numel()) * h.element_size() + 8.0 * L * Cc * P):
+            call("bvae_heads_reparam_kl_bwd", _p(h), _p(wh), _p(eps), _p(mu), _p(logvar), _p(klpd), _p(sc),
+                 _p(lv_pass), _p(g_mu), _p(g_lv), _p(g_z), _p(g_sc), beta, use_cap, cap, cap_w, fb, reg, det, _p(dh),
+                 _p(dwm), _p(dwl), _p(dbm), _p(dbl), _p(ws), ws.numel(), B, L, Cc, P, dt, _stream())
         return (dh, dwm, dbm, dwl, dbl) + (None,) * 12
 
 
@@ -267,24 +321,27 @@ class FcDec(torch.autograd.Function):
         B, L = z.shape
         z = z.contiguous().float()
         h0 = torch.empty((B, Hs, Ws, Cc), dtype=torch_dtype(dt), device=z.device)
-        call("bvae_fc_dec_fwd", _p(z), _p(wd), _p(bd), _p(h0), z_clamp, B, L, Cc * Hs * Ws, dt, _stream())
-        ctx.save_for_backward(z, wd)
+        with profiler.region("fc_dec_fwd", flops=2.0 * B * L * Cc * Hs * Ws,
+                             nbytes=(h0.numel() + wd.numel()) * h0.element_size()):
+            call("bvae_fc_dec_fwd", _p(z), _p(wd), _p(bd), _p(h0), z_clamp, B, L, Cc * Hs * Ws, dt, _stream())
+        ctx.save_for_backward(z, wd, w, b)
         ctx.cfg = (z_clamp, dt, Cc, Hs * Ws)
         return h0
 
     @staticmethod
     def backward(ctx, dh0):
-        z, wd = ctx.saved_tensors
+        z, wd, w, b = ctx.saved_tensors
         z_clamp, dt, Cc, P = ctx.cfg
         B, L = z.shape
         dev = z.device
         dh0 = dh0.contiguous()
         dz = torch.empty((B, L), dtype=torch.float32, device=dev)
-        dw = torch.empty((Cc * P, L), dtype=torch.float32, device=dev)
-        db = torch.empty((Cc * P,), dtype=torch.float32, device=dev)
+        dw, db = grad_out(w), grad_out(b)
         ws = _ws(query("bvae_fc_dec_workspace", B, L, Cc * P), dev)
-        call("bvae_fc_dec_bwd", _p(dh0), _p(z), _p(wd), z_clamp, _p(dz), _p(dw), _p(db), _p(ws), ws.numel(), B, L, Cc,
-             P, dt, _stream())
+        with profiler.region("fc_dec_bwd", flops=4.0 * B * L * Cc * P,
+                             nbytes=(dh0.numel() + wd.numel()) * dh0.element_size() + 4.0 * L * Cc * P):
+            call("bvae_fc_dec_bwd", _p(dh0), _p(z), _p(wd), z_clamp, _p(dz), _p(dw), _p(db), _p(ws), ws.numel(), B, L,
+                 Cc, P, dt, _stream())
         return (dz, dw, db) + (None,) * 7
 
 
@@ -302,9 +359,12 @@ class FinalConvSigmoidRecon(torch.autograd.Function):
         if target is not None:
             target = target.contiguous().float()
         ws = _ws(query("bvae_finalconv_workspace", B, H, W, Cc, Co), dev)
-        call("bvae_finalconv_sigmoid_recon_fwd", _p(h), _p(w), _p(b), _p(target), _p(recon), _p(loss), loss_type,
-             _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
-        ctx.save_for_backward(h, w, recon, target)
+        # algorithmic bytes: read h once, read target, write recon
+        with profiler.region("finalconv_sigmoid_recon_fwd", flops=2.0 * recon.numel() * 9 * Cc,
+                             nbytes=h.numel() * h.element_size() + 8.0 * recon.numel()):
+            call("bvae_finalconv_sigmoid_recon_fwd", _p(h), _p(w), _p(b), _p(target), _p(recon), _p(loss), loss_type,
+                 _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
+        ctx.save_for_backward(h, w, recon, target, b)
         ctx.loss_type = loss_type
         ctx.set_materialize_grads(False)
         if target is None:
@@ -313,7 +373,7 @@ class FinalConvSigmoidRecon(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_recon, g_loss):
-        h, w, recon, target = ctx.saved_tensors
+        h, w, recon, target, b = ctx.saved_tensors
         B, H, W, Cc = h.shape
         Co = w.shape[0]
         dev = h.device
@@ -322,9 +382,11 @@ class FinalConvSigmoidRecon(torch.autograd.Function):
         if g_loss is not None:
             g_loss = g_loss.contiguous().float()
         dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w)
-        db = torch.empty((Co,), dtype=torch.float32, device=dev)
+        dw, db = grad_out(w), grad_out(b)
         ws = _ws(query("bvae_finalconv_workspace", B, H, W, Cc, Co), dev)
-        call("bvae_finalconv_sigmoid_recon_bwd", _p(h), _p(w), _p(recon), _p(target), _p(g_recon), _p(g_loss), _p(dh),
-             _p(dw), _p(db), ctx.loss_type, _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
+        # algorithmic bytes: read h, write dh, read recon/target/g_recon
+        with profiler.region("finalconv_sigmoid_recon_bwd", flops=4.0 * recon.numel() * 9 * Cc,
+                             nbytes=2.0 * h.numel() * h.element_size() + 12.0 * recon.numel()):
+            call("bvae_finalconv_sigmoid_recon_bwd", _p(h), _p(w), _p(recon), _p(target), _p(g_recon), _p(g_loss),
+                 _p(dh), _p(dw), _p(db), ctx.loss_type, _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
         return dh, dw, db, None, None

@@ -23,8 +23,11 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                       \
   } while (0)
 
+extern unsigned long long g_launches;  // kernels launched by this library (bvae_launch_count)
+
 #define BVAE_LAUNCH_CHECK(name)                                  \
   do {                                                           \
+    ++::bvae::g_launches;                                        \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return ::bvae::cuda_fail(e__, name); \
   } while (0)

@@ -7,6 +7,7 @@
 namespace bvae {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(256)
 using namespace bvae;
 
 extern "C" int bvae_version(void) { return 100; }
+extern "C" unsigned long long bvae_launch_count(void) { return g_launches; }
 extern "C" const char* bvae_last_error(void) { return g_err; }
 
 extern "C" int bvae_device_ok(void) {

@@ -42,7 +42,7 @@ static inline bool gn_geom(int P, int C, int vec, GnGeom* g) {
   if (g->cv > kGnThreads) return false;
   g->rows = kGnThreads / g->cv;
   if (g->rows < 1) g->rows = 1;
-  g->threads = g->cv * g->rows;
+  g->threads = (g->cv * g->rows + 31) / 32 * 32;  // whole warps; surplus threads idle (row >= rows)
   g->pc = gn_pixels_per_chunk(P, C);
   g->nchunks = cdiv(P, g->pc);
   return true;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restric
   const T* base = y + ((size_t)b * P) * C + (size_t)col * Vec16<T>::N;
   float s = 0.f, ss = 0.f;
 #pragma unroll 4
-  for (int p = p0 + row; p < p1; p += rows) {
+  for (int p = p0 + row; row < rows && p < p1; p += rows) {
     Vec16<T> v;
     v.load(base + (size_t)p * C);
 #pragma unroll
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   const T* base = y + ((size_t)b * P) * C + (size_t)col * V;
 #pragma unroll 4
-  for (int p = p0 + row; p < p1; p += rows) {
+  for (int p = p0 + row; row < rows && p < p1; p += rows) {
     Vec16<T> v;
     v.load(base + (size_t)p * C);
 #pragma unroll
@@ -135,10 +135,12 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   float* s0 = sm;
   float* s1 = sm + rows * C;
+  if (row < rows) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    s0[row * C + col * V + i] = cnt[i];
-    s1[row * C + col * V + i] = sx[i];
+    for (int i = 0; i < V; ++i) {
+      s0[row * C + col * V + i] = cnt[i];
+      s1[row * C + col * V + i] = sx[i];
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   const size_t off = ((size_t)b * P) * C + (size_t)col * V;
 #pragma unroll 4
-  for (int p = p0 + row; p < p1; p += rows) {
+  for (int p = p0 + row; row < rows && p < p1; p += rows) {
     Vec16<T> v;
     v.load(y + off + (size_t)p * C);
 #pragma unroll
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   const size_t off = ((size_t)b * P) * C + (size_t)col * V;
 #pragma unroll 2
-  for (int p = p0 + row; p < p1; p += rows) {
+  for (int p = p0 + row; row < rows && p < p1; p += rows) {
     Vec16<T> v, d;
     v.load(y + off + (size_t)p * C);
     d.load(dout + off + (size_t)p * C);
@@ -271,10 +273,12 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   float* s0 = sm;
   float* s1 = sm + rows * C;
+  if (row < rows) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    s0[row * C + col * V + i] = a1[i];
-    s1[row * C + col * V + i] = a2[i];
+    for (int i = 0; i < V; ++i) {
+      s0[row * C + col * V + i] = a1[i];
+      s1[row * C + col * V + i] = a2[i];
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   const size_t off = ((size_t)b * P) * C + (size_t)col * V;
 #pragma unroll 2
-  for (int p = p0 + row; p < p1; p += rows) {
+  for (int p = p0 + row; row < rows && p < p1; p += rows) {
     Vec16<T> v, d;
     v.load(y + off + (size_t)p * C);
     d.load(dout + off + (size_t)p * C);

@@ -44,6 +44,8 @@ int bvae_version(void);
 const char* bvae_last_error(void);
 /* 1 when the device behind the current context is compute capability 10.x */
 int bvae_device_ok(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+unsigned long long bvae_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Weight packing: fp32 master parameters (reference layout) -> compute copies.

@@ -125,6 +125,8 @@ def spec_from_config(cfg) -> PathSpec:
 def group_norm_1(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
     """nn.GroupNorm(1, C): one group = per-sample statistics over C*H*W, biased variance,
     per-channel affine (beta_vae.py:20-21)."""
+    if x.dtype in (torch.bfloat16, torch.float16):
+        x = x.float()          # autocast runs group_norm in fp32 (ATen autocast fp32 list)
     n = x.shape[0]
     flat = x.reshape(n, -1)
     mean = flat.mean(dim=1)
@@ -188,6 +190,8 @@ def encode(sd: Dict[str, torch.Tensor], spec: PathSpec, x: torch.Tensor):
     h = h.reshape(h.shape[0], -1)               # NCHW flatten: feature = c*H*W + y*W + x
     mu = h @ sd["fc_mu.weight"].t() + sd["fc_mu.bias"]
     logvar = h @ sd["fc_logvar.weight"].t() + sd["fc_logvar.bias"]
+    if mu.dtype in (torch.bfloat16, torch.float16):   # under autocast exp/pow/sum run in fp32
+        mu, logvar = mu.float(), logvar.float()
     lo, hi = spec.logvar_clamp if spec.logvar_clamp else (-10.0, 10.0)
     logvar = torch.clamp(logvar, lo, hi)        # gradient is zero outside [lo, hi]
     return mu, logvar
@@ -238,8 +242,9 @@ def reconstruction_loss(spec: PathSpec, recon, x):
 
 def focal_frequency_loss(pred, target, alpha: float = 1.0, eps: float = 1e-8):
     """FocalFrequencyLoss.forward (losses.py:16-35): the weight is NOT detached."""
-    pf = torch.fft.fft2(pred.float(), norm="ortho")
-    tf = torch.fft.fft2(target.float(), norm="ortho")
+    up = (lambda t: t) if pred.dtype == torch.float64 else (lambda t: t.float())
+    pf = torch.fft.fft2(up(pred), norm="ortho")
+    tf = torch.fft.fft2(up(target), norm="ortho")
     d = pf - tf
     dist = d.real.pow(2) + d.imag.pow(2)
     denom = dist.mean(dim=(0, 2, 3), keepdim=True) + eps
@@ -285,10 +290,19 @@ def loss(sd, spec: PathSpec, x, eps, beta=1.0, capacity=None, free_bits=0.0, cap
     }
 
 
-def loss_and_grads(sd, spec: PathSpec, x, eps, **kw):
-    """fwd + bwd: returns (loss dict with detached tensors, {key: grad})."""
-    leaf = {k: v.detach().clone().float().requires_grad_(True) for k, v in sd.items()}
-    out = loss(leaf, spec, x.float(), None if eps is None else eps.float(), **kw)
+def loss_and_grads(sd, spec: PathSpec, x, eps, precision="fp32", **kw):
+    """fwd + bwd: returns (loss dict with detached tensors, {key: grad}).
+    precision: "fp32" (the reference with mixed_precision: false), "fp64" (exact answer),
+    "bf16" (the reference's arithmetic under torch.autocast(cpu, bfloat16): conv / linear in
+    bf16, normalisation / loss math in fp32 -- used to size the bf16 tolerance)."""
+    dt = torch.float64 if precision == "fp64" else torch.float32
+    leaf = {k: v.detach().clone().to(dt).requires_grad_(True) for k, v in sd.items()}
+    xe, ee = x.to(dt), None if eps is None else eps.to(dt)
+    if precision == "bf16":
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out = loss(leaf, spec, xe, ee, **kw)
+    else:
+        out = loss(leaf, spec, xe, ee, **kw)
     out["total"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
     det = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}

@@ -42,6 +42,15 @@ def weight_init(m):  # what src/training/train.py:217-221 applies; restated, not
             torch.nn.init.zeros_(m.bias)
 
 
+def ffl64(pred, target, alpha, eps):
+    """The reference's FocalFrequencyLoss hard-casts to float32 (losses.py:20-21); for the fp64
+    run the same formula is evaluated without that cast."""
+    d = torch.fft.fft2(pred, norm="ortho") - torch.fft.fft2(target, norm="ortho")
+    dist = d.real.pow(2) + d.imag.pow(2)
+    denom = dist.mean(dim=(0, 2, 3), keepdim=True) + eps
+    return ((dist / denom).clamp_min(eps).pow(alpha) * dist).mean()
+
+
 def base_cfg(**over):
     cfg = {
         "data": {"image_size": 32, "grayscale": True},
@@ -82,7 +91,10 @@ SMALL_CASES = {
 }
 
 
-def run_reference(cfg_obj, seed, batch, kw, logvar_scale=None):
+def run_reference(cfg_obj, seed, batch, kw, logvar_scale=None, mode="fp32"):
+    """mode: fp32 (the reference as shipped for mixed_precision: false), fp64 (same module in
+    double: the exact answer both fp32 implementations approximate), bf16 (the reference under
+    torch.autocast(cpu, bfloat16): how far the reference's own low-precision run is from exact)."""
     torch.manual_seed(seed)
     m = BetaVAE(cfg_obj)
     m.apply(weight_init)
@@ -102,7 +114,17 @@ def run_reference(cfg_obj, seed, batch, kw, logvar_scale=None):
     x = torch.rand(batch, in_ch, size, size, generator=g)
     eps = torch.randn(batch, m.latent_dim, generator=g)
     m.reparameterize = lambda mu, logvar: mu + eps * torch.exp(0.5 * logvar)
-    out = m.loss(x, **kw)
+    if mode == "fp64":
+        m = m.double()
+        x, eps = x.double(), eps.double()
+        m.reparameterize = lambda mu, logvar: mu + eps * torch.exp(0.5 * logvar)
+        m.ffl_loss.forward = lambda p, t: ffl64(p, t, m.ffl_loss.alpha, m.ffl_loss.eps)
+        out = m.loss(x, **kw)
+    elif mode == "bf16":
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out = m.loss(x, **kw)
+    else:
+        out = m.loss(x, **kw)
     out["total"].backward()
     grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p))
              for k, p in m.named_parameters()}
@@ -121,8 +143,16 @@ def main():
                 keep[k] = v.detach().clone()
             else:
                 keep[k] = v
+        _, _, _, _, out64, grads64 = run_reference(ns(cfg), seed=7, batch=batch, kw=kw, logvar_scale=6.0, mode="fp64")
+        extra = {"grads64": {k: v.float() for k, v in grads64.items()},
+                 "grads64_resid": {k: (v - v.float().double()).float() for k, v in grads64.items()},
+                 "total64": float(out64["total"])}
+        if cfg["model"]["reconstruction_loss"] != "bce":
+            _, _, _, _, outb, gradsb = run_reference(ns(cfg), seed=7, batch=batch, kw=kw, logvar_scale=6.0, mode="bf16")
+            extra["grads_bf16"] = {k: v.float() for k, v in gradsb.items()}
+            extra["total_bf16"] = float(outb["total"])
         torch.save({"cfg": cfg, "loss_kwargs": kw, "state": sd, "x": x, "eps": eps,
-                    "out": keep, "grads": grads}, os.path.join(HERE, f"small_{name}.pt"))
+                    "out": keep, "grads": grads, **extra}, os.path.join(HERE, f"small_{name}.pt"))
         print(name, "total", float(out["total"]), "kl", float(out["kl_mean"]))
 
     full = {}

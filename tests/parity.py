@@ -29,3 +29,25 @@ def check(name, got, ref, rtol, gnorm=0.0, floor=0.0):
     bound = rtol * float(ref_d.norm()) + floor * gnorm
     assert err <= bound or err == 0.0, f"{name}: |err|={err:.3e} > bound {bound:.3e} (rel {rel_err(got, ref):.3e})"
     return rel_err(got, ref)
+
+
+def check_vs_exact(name, got, ref_lp, exact, rtol, gnorm=0.0, floor=0.0, slack=1.5):
+    """Parity for tensors whose low-precision *reference* value is itself noisy.
+
+    ``exact`` is the same computation in fp64 (reference module in double / oracle in double),
+    ``ref_lp`` the reference at the precision under test (fp32, or bf16 autocast).  ``got``
+    passes when it is within ``rtol`` of the exact answer (plus the floor above), or -- for
+    ill-conditioned tensors where even the reference is further than that from exact, e.g. the
+    first conv's weight gradient (sum of x*dy with sum(dy) ~ 0 after GroupNorm) -- when it is no
+    further from exact than ``slack`` x the reference's own error.  Returns (err_got, err_ref)
+    as fractions of ||exact||."""
+    g, r, e = (t.detach().double().cpu() for t in (got, ref_lp, exact))
+    assert g.shape == e.shape, (name, g.shape, e.shape)
+    assert torch.isfinite(g).all(), f"{name}: non-finite values"
+    n = float(e.norm())
+    e_got, e_ref = float((g - e).norm()), float((r - e).norm())
+    bound = max(rtol * n + floor * gnorm, slack * e_ref)
+    assert e_got <= bound, (f"{name}: |got-exact|={e_got:.3e} > max(rtol*|exact|+floor={rtol * n + floor * gnorm:.3e}, "
+                            f"{slack}*|ref-exact|={slack * e_ref:.3e})  (|exact|={n:.3e})")
+    d = n if n > 0 else 1.0
+    return e_got / d, e_ref / d
