@@ -113,6 +113,11 @@ class PackCache:
         return val
 
 
+def conv_weight_layout(H, W, Cin, Cout, stride, dt, kind):
+    """0 -> [t][k][n] pack (CUDA-core kernels), 1 -> [t][n][k] pack (tcgen05 kernels); kind 0 fprop, 1 dgrad."""
+    return query("bvae_conv3x3_weight_layout", H, W, Cin, Cout, stride, dt, kind)
+
+
 def pack_conv(w, dt, transpose, layout=0):
     cout, cin = w.shape[0], w.shape[1]
     k, n = (cout, cin) if transpose else (cin, cout)
@@ -244,8 +249,14 @@ class ConvGnSeBlock(torch.autograd.Function):
     decoder DeconvBlock of the reference (src/models/beta_vae.py:33-66)."""
 
     @staticmethod
-    def forward(ctx, x, cw, cb, gw, gb, w1, b1, w2, b2, wp, wpt, stride, upsample, dt):
+    def forward(ctx, x, cw, cb, gw, gb, w1, b1, w2, b2, packs, key, stride, upsample, dt):
         xin = upsample2x_fwd(x) if upsample else x
+        _, H, W, Cin = xin.shape
+        Cout = cw.shape[0]
+        lf = conv_weight_layout(H, W, Cin, Cout, stride, dt if code_of(xin) == dt else F32, 0)
+        lb = conv_weight_layout(H, W, Cin, Cout, stride, dt, 1)
+        wp = packs.get(f"{key}.fprop.{lf}", (cw,), dt, lambda: pack_conv(cw, dt, False, lf))
+        wpt = packs.get(f"{key}.dgrad.{lb}", (cw,), dt, lambda: pack_conv(cw, dt, True, lb))
         y = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt)
         out, saved = gn_relu_se_fwd(y, gw, gb, w1, b1, w2, b2)
         stats, cpos, spos, hidden, gate = saved

@@ -15,7 +15,10 @@
 //            di = (po+1-r)/2, ss = 1, ds = 2   (a transposed conv as 4 dense sub-convs)
 // Tile: 128 output pixels x 64 channels per CTA, 8x4 outputs per thread, BK = 16 channels of
 // one tap per step, double-buffered shared memory with register prefetch.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace bvae {
 
@@ -403,12 +406,12 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < V; ++k) sm[row * Cout + col * V + k] = (t < 9) ? acc[t < 9 ? t : 0][k] : bs[k];
     __syncthreads();
     for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
-      float a = 0.f;
-      for (int r = 0; r < rows; ++r) a += sm[r * Cout + c];
+      double a = 0.0;  // x > 0 and sum(dy) ~ 0 after GroupNorm: keep the cancellation exact-ish
+      for (int r = 0; r < rows; ++r) a += (double)sm[r * Cout + c];
       if (t < 9)
-        part[(((size_t)chunk * Cin + ci) * 9 + t) * Cout + c] = a;
+        part[(((size_t)chunk * Cin + ci) * 9 + t) * Cout + c] = (float)a;
       else if (ci == 0 && bpart)
-        bpart[(size_t)chunk * Cout + c] = a;
+        bpart[(size_t)chunk * Cout + c] = (float)a;
     }
   }
 }
@@ -425,9 +428,9 @@ __global__ void __launch_bounds__(256)
       const int co = (int)(i % Cout);
       const int t = (int)((i / Cout) % 9);
       const int ci = (int)(i / (9LL * Cout));
-      float acc = 0.f;
-      for (int s = 0; s < chunks; ++s) acc += part[(size_t)s * total + i];
-      dw[((size_t)co * Cin + ci) * 9 + t] = acc;
+      double acc = 0.0;
+      for (int s = 0; s < chunks; ++s) acc += (double)part[(size_t)s * total + i];
+      dw[((size_t)co * Cin + ci) * 9 + t] = (float)acc;
     } else if (dbias) {
       const int co = (int)(i - total);
       float acc = 0.f;
@@ -519,6 +522,15 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, float* dbias, 
 
 using namespace bvae;
 
+// 1 -> the tcgen05 kernels serve this shape and expect the [t][n][k] pack; 0 -> CUDA-core kernels, [t][k][n].
+// BVAE_CONV_SIMT=1 in the environment pins everything to the CUDA-core kernels (debugging aid).
+extern "C" int bvae_conv3x3_weight_layout(int H, int W, int Cin, int Cout, int stride, int dtype, int kind) {
+  const char* env = getenv("BVAE_CONV_SIMT");  // read per call so tests can flip it
+  if ((env != nullptr && env[0] == '1') || dtype != BVAE_BF16) return 0;
+  if (stride != 1 && stride != 2) return 0;
+  return conv_tc_supported(H, W, Cin, Cout, stride, kind) ? 1 : 0;
+}
+
 extern "C" int bvae_conv3x3_fprop(const void* x, const void* wp, const float* bias, void* y, int B, int H, int W,
                                   int Cin, int Cout, int stride, int x_dtype, int y_dtype, bvae_stream_t stream) {
   BVAE_REQUIRE(x && wp && y, BVAE_ERR_ARG, "conv3x3_fprop: null pointer");
@@ -526,6 +538,8 @@ extern "C" int bvae_conv3x3_fprop(const void* x, const void* wp, const float* bi
   BVAE_REQUIRE(stride == 1 || stride == 2, BVAE_ERR_UNSUPPORTED, "conv3x3_fprop: stride %d", stride);
   cudaStream_t st = as_stream(stream);
   const int Ho = conv_out(H, stride), Wo = conv_out(W, stride);
+  if (bvae_conv3x3_weight_layout(H, W, Cin, Cout, stride, x_dtype == y_dtype ? x_dtype : BVAE_F32, 0) == 1)
+    return conv_tc_fprop(x, wp, bias, y, B, H, W, Cin, Cout, stride, st);  // tcgen05 path, wp is the [t][n][k] pack
   if (Cin % 4 != 0) {  // first layer: direct kernel; x may be the fp32 input image
     BVAE_REQUIRE(Cin == 1 || Cin == 3, BVAE_ERR_UNSUPPORTED, "conv3x3_fprop: Cin=%d (need 1, 3 or a multiple of 4)", Cin);
     const size_t sm = (size_t)(9 * Cin + 1) * Cout * sizeof(float);
@@ -575,6 +589,8 @@ extern "C" int bvae_conv3x3_dgrad(const void* dy, const void* wp_t, void* dx, in
                "conv3x3_dgrad: Cin=%d Cout=%d must be multiples of 4", Cin, Cout);
   cudaStream_t st = as_stream(stream);
   const int Ho = conv_out(H, stride), Wo = conv_out(W, stride);
+  if (bvae_conv3x3_weight_layout(H, W, Cin, Cout, stride, dtype, 1) == 1)
+    return conv_tc_dgrad(dy, wp_t, dx, B, H, W, Cin, Cout, stride, st);  // tcgen05 path, wp_t is the [t][n][k] pack
   TapGemm p;
   p.src = dy; p.wp = wp_t; p.bias = nullptr; p.dst = dx;
   p.B = B; p.IH = Ho; p.IW = Wo; p.K = Cout;

@@ -1,0 +1,44 @@
+// Shared declarations of the tcgen05 convolution kernels (conv_tc.cu, conv_tc_wgrad.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace bvae {
+
+struct TcTap {
+  int8_t map;   // which source tensor map (stride-2 fprop: parity view ph*2+pw)
+  int8_t di;    // row offset of the tap in the source grid
+  int8_t dj;    // column offset
+  int8_t widx;  // weight slice r*3+s
+};
+
+struct TcMaps {
+  CUtensorMap src[4];
+  CUtensorMap w;
+};
+
+struct TcParams {
+  int ntaps;
+  TcTap taps[9];
+  int kc, kchunks;               // channels per chunk (64/32/16) and chunks per tap
+  int bn;                        // output channels per CTA (UMMA N)
+  int tw, th, tn;                // tile box: tw*th*tn = 128 pixels
+  int tiles_w, tiles_h;
+  int B, N;                      // batch, total output channels
+  int DH, DW, ds, po, pw;        // destination tensor and scatter (dst row = oi*ds + po)
+  int stages, tmem_cols;
+  __nv_bfloat16* dst;
+  const float* bias;
+};
+
+// kind 0 = fprop, 1 = dgrad.  True when the tcgen05 kernel covers the shape (bf16 only).
+bool conv_tc_supported(int H, int W, int Cin, int Cout, int stride, int kind);
+int conv_tc_fprop(const void* x, const void* wp_nk, const float* bias, void* y, int B, int H, int W, int Cin,
+                  int Cout, int stride, cudaStream_t st);
+int conv_tc_dgrad(const void* dy, const void* wpt_nk, void* dx, int B, int H, int W, int Cin, int Cout, int stride,
+                  cudaStream_t st);
+
+}  // namespace bvae

@@ -144,14 +144,14 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, q = 0.f;
+    double a = 0.0, q = 0.0;  // fixed-order, double: these sums cancel heavily downstream
     for (int r = 0; r < rows; ++r) {
-      a += s0[r * C + c];
-      q += s1[r * C + c];
+      a += (double)s0[r * C + c];
+      q += (double)s1[r * C + c];
     }
     const size_t o = ((size_t)b * nchunks + chunk) * C + c;
-    cpart[o] = a;
-    xpart[o] = q;
+    cpart[o] = (float)a;
+    xpart[o] = (float)q;
   }
 }
 
@@ -282,14 +282,14 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, q = 0.f;
+    double a = 0.0, q = 0.0;  // fixed-order, double: these sums cancel heavily downstream
     for (int r = 0; r < rows; ++r) {
-      a += s0[r * C + c];
-      q += s1[r * C + c];
+      a += (double)s0[r * C + c];
+      q += (double)s1[r * C + c];
     }
     const size_t o = ((size_t)b * nchunks + chunk) * C + c;
-    a1part[o] = a;
-    a2part[o] = q;
+    a1part[o] = (float)a;
+    a2part[o] = (float)q;
   }
 }
 
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256)
                       float* __restrict__ G2o, float* __restrict__ dz2o, float* __restrict__ dz1o,
                       float* __restrict__ dpoolo, float* __restrict__ coef, int P, int C, int R) {
   extern __shared__ float sm[];  // A1[C] A2[C] dz2[C] dz1[R]
-  __shared__ float red[32];
+  __shared__ double red[32];
   float* A1 = sm;
   float* A2 = sm + C;
   float* dz2 = sm + 2 * C;
@@ -316,12 +316,13 @@ __global__ void __launch_bounds__(256)
   const int b = blockIdx.x;
   const bool has_se = (w1 != nullptr);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, q = 0.f;
+    double ad = 0.0, qd = 0.0;
     for (int k = 0; k < nchunks; ++k) {
       const size_t o = ((size_t)b * nchunks + k) * C + c;
-      a += a1part[o];
-      q += a2part[o];
+      ad += (double)a1part[o];
+      qd += (double)a2part[o];
     }
+    const float a = (float)ad, q = (float)qd;
     A1[c] = a;
     A2[c] = q;
     if (has_se) {
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
-  float s1 = 0.f, s2 = 0.f;
+  double s1 = 0.0, s2 = 0.0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float g1, g2;
     if (has_se) {
@@ -364,14 +365,14 @@ __global__ void __launch_bounds__(256)
     }
     G1o[(size_t)b * C + c] = g1;
     G2o[(size_t)b * C + c] = g2;
-    s1 = fmaf(gamma[c], g1, s1);
-    s2 = fmaf(gamma[c], g2, s2);
+    s1 += (double)gamma[c] * (double)g1;
+    s2 += (double)gamma[c] * (double)g2;
   }
   s1 = block_sum(s1, red);
   s2 = block_sum(s2, red);
   if (threadIdx.x == 0) {
-    coef[2 * b] = s1;
-    coef[2 * b + 1] = s2;
+    coef[2 * b] = (float)s1;
+    coef[2 * b + 1] = (float)s2;
   }
 }
 

@@ -74,11 +74,9 @@ class _FusedBlock(nn.Module):
 
     def forward(self, x, packs: ops.PackCache, key: str, dt: int):
         conv = self._conv()
-        wp = packs.get(key + ".fprop", (conv.weight,), dt, lambda: ops.pack_conv(conv.weight, dt, False))
-        wpt = packs.get(key + ".dgrad", (conv.weight,), dt, lambda: ops.pack_conv(conv.weight, dt, True))
         w1, b1, w2, b2 = self.se.gate_params
         return ops.ConvGnSeBlock.apply(x, conv.weight, conv.bias, self.norm.weight, self.norm.bias, w1, b1, w2, b2,
-                                       wp, wpt, self.stride, self.upsample, dt)
+                                       packs, key, self.stride, self.upsample, dt)
 
 
 class ConvBlock(_FusedBlock):

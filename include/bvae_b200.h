@@ -69,6 +69,9 @@ int bvae_pack_fcdec_weight(const float* w, const float* b, void* wd, float* bd, 
  * backward = what autograd's convolution_backward computes for them).
  *   x  [B][H][W][Cin], y [B][Ho][Wo][Cout], Ho = (H-1)/stride + 1.
  * ---------------------------------------------------------------------------------------- */
+/* Which weight pack the kernels want for this shape: 1 = [t][n][k] (tcgen05 implicit GEMM, bf16),
+ * 0 = [t][k][n] (CUDA-core kernels: fp32, odd shapes).  kind: 0 = fprop, 1 = dgrad. */
+int bvae_conv3x3_weight_layout(int H, int W, int Cin, int Cout, int stride, int dtype, int kind);
 int bvae_conv3x3_fprop(const void* x, const void* wp, const float* bias, void* y, int B, int H, int W,
                        int Cin, int Cout, int stride, int x_dtype, int y_dtype, bvae_stream_t stream);
 /* dx = conv_transpose(dy, w); wp_t is the layout-0, transpose=1 pack. */

@@ -34,6 +34,26 @@ def rnd(x, dtype):           # value as the kernel sees it
     return x.to(dtype).float()
 
 
+import os
+
+
+class conv_path:
+    """Pin the bf16 convolutions to the CUDA-core kernels ("simt") or leave the tcgen05 dispatch on ("tc")."""
+
+    def __init__(self, which):
+        self.which = which
+
+    def __enter__(self):
+        self.old = os.environ.get("BVAE_CONV_SIMT")
+        os.environ["BVAE_CONV_SIMT"] = "1" if self.which == "simt" else "0"
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("BVAE_CONV_SIMT", None)
+        else:
+            os.environ["BVAE_CONV_SIMT"] = self.old
+
+
 CONV_SHAPES = [
     # B, H, W, Cin, Cout, stride
     (2, 8, 8, 8, 16, 1),
@@ -45,12 +65,26 @@ CONV_SHAPES = [
     (1, 1, 1, 8, 8, 1),       # 1x1 image: only the centre tap is in range
     (2, 6, 6, 72, 40, 1),     # channel counts that are not multiples of the tile sizes
     (130, 2, 2, 8, 8, 1),     # more than one M tile from the batch dimension
+    # shapes the tcgen05 kernels take in bf16 (power-of-two grids, channels 16/32/64k)
+    (2, 16, 16, 64, 64, 1),
+    (3, 8, 8, 128, 256, 1),   # tile spans two samples, odd batch -> zero-filled tail rows
+    (2, 16, 16, 64, 128, 2),
+    (1, 32, 32, 16, 32, 2),   # 32-byte swizzle (Cin = 16), 64-byte swizzle on dgrad (Cout = 32)
+    (2, 4, 4, 512, 512, 1),   # 8 channel chunks per tap, two N tiles
+    (1, 128, 128, 64, 64, 1), # one image row per tile
+    (2, 256, 256, 16, 16, 1), # two tiles per image row
+    (5, 2, 2, 64, 64, 2),     # 1x1 output grid per sample
 ]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16-simt"])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 def test_conv3x3_fprop_dgrad_wgrad(shape, prec):
+    with conv_path("simt" if prec.endswith("simt") else "tc"):
+        _conv_case(shape, prec.split("-")[0])
+
+
+def _conv_case(shape, prec):
     ops = _ops()
     dtype, tol = DT[prec]
     dt = ops.BF16 if prec == "bf16" else ops.F32
@@ -68,8 +102,8 @@ def test_conv3x3_fprop_dgrad_wgrad(shape, prec):
     yr.backward(dy)
 
     wd = w.to(dev())
-    wp = ops.pack_conv(wd, dt, False)
-    wpt = ops.pack_conv(wd, dt, True)
+    wp = ops.pack_conv(wd, dt, False, ops.conv_weight_layout(H, W, Cin, Cout, s, dt, 0))
+    wpt = ops.pack_conv(wd, dt, True, ops.conv_weight_layout(H, W, Cin, Cout, s, dt, 1))
     xd = nhwc(x, dtype)
     y = ops.conv3x3_fprop(xd, wp, b.to(dev()), Cout, s, dt)
     assert rel_err(nchw(y), yr) <= tol
