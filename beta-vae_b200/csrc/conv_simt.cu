@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256)
 // dw[co][ci][t] = sum_split part[split][t][ci][co];  dbias[co] = sum_split bpart[split][co]
 __global__ void __launch_bounds__(256)
     conv_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart, float* __restrict__ dw,
-                             float* __restrict__ dbias, int Cin, int Cout, int splits) {
+                             float* __restrict__ dbias, int Cin, int Cout, int splits, int bsplits) {
   const long long total = 9LL * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + Cout;
        i += (long long)gridDim.x * blockDim.x) {
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256)
     } else if (dbias) {
       const int co = (int)(i - total);
       float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += bpart[(size_t)s * Cout + co];
+      for (int s = 0; s < bsplits; ++s) acc += bpart[(size_t)s * Cout + co];
       dbias[co] = acc;
     }
   }
@@ -513,7 +513,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, float* dbias, 
   const long long total = 9LL * Cin * Cout + Cout;
   long long blocks = (total + 255) / 256;
   if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-  conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits);
+  conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.splits);
   BVAE_LAUNCH_CHECK("conv_wgrad_reduce");
   return BVAE_OK;
 }
@@ -630,9 +630,20 @@ extern "C" int bvae_conv3x3_dgrad(const void* dy, const void* wp_t, void* dx, in
   return BVAE_OK;
 }
 
+static bool wgrad_uses_tc(int H, int W, int Cin, int Cout, int stride, int x_dtype, int dy_dtype) {
+  const char* env = getenv("BVAE_CONV_SIMT");
+  if (env != nullptr && env[0] == '1') return false;
+  return x_dtype == BVAE_BF16 && dy_dtype == BVAE_BF16 && conv_tc_wgrad_supported(H, W, Cin, Cout, stride);
+}
+
 extern "C" size_t bvae_conv3x3_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int stride) {
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (stride != 1 && stride != 2)) return 0;
-  return wgrad_plan(B, H, W, Cin, Cout, stride).bytes;
+  size_t bytes = wgrad_plan(B, H, W, Cin, Cout, stride).bytes;
+  if (conv_tc_wgrad_supported(H, W, Cin, Cout, stride)) {  // dtype is not known here: cover both kernels
+    const WgradTcPlan pl = conv_tc_wgrad_plan(B, H, W, Cin, Cout, stride);
+    if (pl.part_bytes + pl.bpart_bytes > bytes) bytes = pl.part_bytes + pl.bpart_bytes;
+  }
+  return bytes;
 }
 
 extern "C" int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, float* dbias, void* ws, size_t ws_bytes,
@@ -644,6 +655,19 @@ extern "C" int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, floa
   BVAE_REQUIRE(ws_bytes >= bvae_conv3x3_wgrad_workspace(B, H, W, Cin, Cout, stride), BVAE_ERR_WORKSPACE,
                "conv3x3_wgrad: workspace too small");
   cudaStream_t st = as_stream(stream);
+  if (wgrad_uses_tc(H, W, Cin, Cout, stride, x_dtype, dy_dtype)) {  // tcgen05 path
+    const WgradTcPlan pl = conv_tc_wgrad_plan(B, H, W, Cin, Cout, stride);
+    float* part = reinterpret_cast<float*>(ws);
+    float* bpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
+    const int rc = conv_tc_wgrad(x, dy, part, dbias ? bpart : nullptr, pl, B, H, W, Cin, Cout, stride, st);
+    if (rc != BVAE_OK) return rc;
+    const long long total = 9LL * Cin * Cout + Cout;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks);
+    BVAE_LAUNCH_CHECK("conv_wgrad_reduce");
+    return BVAE_OK;
+  }
   if (x_dtype == BVAE_F32 && dy_dtype == BVAE_F32)
     return wgrad_launch<float, float>(x, dy, dw, dbias, ws, B, H, W, Cin, Cout, stride, st);
   if (x_dtype == BVAE_BF16 && dy_dtype == BVAE_BF16)

@@ -41,4 +41,16 @@ int conv_tc_fprop(const void* x, const void* wp_nk, const float* bias, void* y, 
 int conv_tc_dgrad(const void* dy, const void* wpt_nk, void* dx, int B, int H, int W, int Cin, int Cout, int stride,
                   cudaStream_t st);
 
+// ---- wgrad (conv_tc_wgrad.cu) ----
+struct WgradTcPlan {
+  int bn, slots, groups;           // co tile, accumulator slots per CTA, row-block groups
+  int tiles_total, tiles_per_split, splits;
+  int bias_chunks, bias_pix_per_chunk;
+  size_t part_bytes, bpart_bytes;  // workspace: partial dW [split][9][Cin][Cout], partial db [chunk][Cout]
+};
+bool conv_tc_wgrad_supported(int H, int W, int Cin, int Cout, int stride);
+WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int stride);
+int conv_tc_wgrad(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
+                  int W, int Cin, int Cout, int stride, cudaStream_t st);
+
 }  // namespace bvae

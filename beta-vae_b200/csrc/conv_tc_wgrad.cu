@@ -1,0 +1,313 @@
+// Weight gradient of the 3x3 convolutions on the 5th-generation tensor cores.
+//   dW[t][ci][co] = sum over output pixels p of  x[p + off_t][ci] * dy[p][co]
+// (what convolution_backward computes for nn.Conv2d at src/models/beta_vae.py:37,42,54).
+//
+// GEMM view: the reduction (K) runs over PIXELS, so both operands are "MN-major": a TMA box of
+// NHWC data -- 64 pixels x 64 channels, one 128-byte row per pixel -- is exactly the 128B-swizzled
+// MN-major layout tcgen05.mma reads.  No transposes, no im2col.
+//   A (M = 128 rows)  : two 64-channel x-boxes stacked along M.  A "unit" is (tap, 64-channel chunk
+//                       of Cin); a 128-row block holds units 2*rb and 2*rb+1, so with Cin = 64 one
+//                       MMA covers two taps, with Cin >= 128 two channel chunks of one tap.
+//   B (N = BN <= 256) : the dy box(es) of the same 64 pixels, BN/64 boxes side by side.
+//   D                 : up to 512/BN accumulator slots live in TMEM at once, each [128 x BN] fp32;
+//                       one dy tile is reused by all slots of the CTA.
+// Stride-2 convolutions read x through the four parity tensor maps (see conv_tc.cu).
+// Split-K: every CTA owns a contiguous range of 64-pixel tiles; partial results go to the fp32
+// workspace [split][tap][ci][co] that the (deterministic) reduce kernel of conv_simt.cu sums.
+// Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace bvae {
+
+static constexpr int WG_THREADS = 192;
+static constexpr int WG_PIX = 64;                    // pixels per pipeline stage
+static constexpr uint32_t WG_BOX = WG_PIX * 64 * 2;  // bytes of one 64-pixel x 64-channel box (8 KB)
+
+struct WgParams {
+  TcTap taps[9];
+  int cin_chunks, units;  // Cin/64, 9*Cin/64
+  int slots;              // accumulator slots per CTA
+  int bn;                 // co tile
+  int tw, th, tn, tiles_w, tiles_h, tiles_total, tiles_per_split;
+  int B, Cin, Cout;
+  int stages, tmem_cols;
+  float* part;
+};
+
+struct WgMaps {
+  CUtensorMap x[4];
+  CUtensorMap dy;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nb = p.bn / 64;                                      // dy boxes per stage
+  const uint32_t stage_bytes = (uint32_t)(nb + 2 * p.slots) * WG_BOX;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* accum_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb0 = blockIdx.x * p.slots;  // first 128-row block of this CTA
+  const int n0 = blockIdx.y * p.bn;
+  const int split = blockIdx.z;
+  const int t_beg = split * p.tiles_per_split;
+  const int t_end = min(p.tiles_total, t_beg + p.tiles_per_split);
+  const int iters = t_end - t_beg;
+  // valid units of this CTA (the last row block may be half empty, the last group short)
+  int nslots = 0;
+  for (int s = 0; s < p.slots; ++s)
+    if (2 * (rb0 + s) < p.units) nslots = s + 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && iters > 0) {
+      int nunits = 0;
+      for (int s = 0; s < nslots; ++s)
+        for (int h = 0; h < 2; ++h)
+          if (2 * (rb0 + s) + h < p.units) ++nunits;
+      const uint32_t tx_bytes = (uint32_t)(nb + nunits) * WG_BOX;
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        int tile = t_beg + it;
+        const int w0 = (tile % p.tiles_w) * p.tw;
+        tile /= p.tiles_w;
+        const int h0 = (tile % p.tiles_h) * p.th;
+        const int b0 = (tile / p.tiles_h) * p.tn;
+        uint8_t* base = smem + (size_t)st * stage_bytes;
+        mbar_expect_tx(&full_bar[st], tx_bytes);
+        for (int j = 0; j < nb; ++j) tma_load_4d(&maps.dy, &full_bar[st], base + (size_t)j * WG_BOX, n0 + 64 * j, w0, h0, b0);
+        uint8_t* xb = base + (size_t)nb * WG_BOX;
+        for (int s = 0; s < nslots; ++s)
+          for (int h = 0; h < 2; ++h) {
+            const int u = 2 * (rb0 + s) + h;
+            if (u >= p.units) continue;
+            const TcTap tap = p.taps[u / p.cin_chunks];
+            tma_load_4d(&maps.x[tap.map], &full_bar[st], xb + (size_t)(2 * s + h) * WG_BOX, (u % p.cin_chunks) * 64,
+                        w0 + tap.dj, h0 + tap.di, b0);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && iters > 0) {
+      // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t dy_addr = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t x_addr = dy_addr + (uint32_t)nb * WG_BOX;
+        for (int s = 0; s < nslots; ++s) {
+#pragma unroll
+          for (int k = 0; k < WG_PIX / 16; ++k) {
+            // 16 pixels = 16 rows of 128 bytes = two swizzle atoms: advance 2048 bytes per K step
+            const uint64_t adesc = mnmajor_desc(x_addr + (uint32_t)(2 * s) * WG_BOX + k * 2048u, WG_BOX, 1024u);
+            const uint64_t bdesc = mnmajor_desc(dy_addr + k * 2048u, WG_BOX, 1024u);
+            umma_bf16(tmem_base + (uint32_t)(s * p.bn), adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[st]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else if (iters > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // accumulator row: unit half (m / 64), channel within chunk (m % 64)
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    for (int s = 0; s < nslots; ++s) {
+      const int u = 2 * (rb0 + s) + (m >> 6);
+      const bool valid = u < p.units;
+      const int tap = valid ? p.taps[u / p.cin_chunks].widx : 0;
+      const int ci = valid ? (u % p.cin_chunks) * 64 + (m & 63) : 0;
+      float* out = p.part + (((size_t)split * 9 + tap) * p.Cin + ci) * p.Cout + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * p.bn);
+      for (int c = 0; c < p.bn; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(out + c + g * 4) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Column sums of dy (bias gradient), fp32 partials [chunk][C]; memory bound, one pass over dy.
+__global__ void __launch_bounds__(256)
+    colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ bpart, long long npix, int C, int cv,
+                       int rows, int pix_per_chunk) {
+  extern __shared__ float sm[];
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const long long p0 = (long long)blockIdx.x * pix_per_chunk, p1 = min(npix, p0 + pix_per_chunk);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (long long p = p0 + row; row < rows && p < p1; p += rows) {
+    Vec16<__nv_bfloat16> v;
+    v.load(dy + (size_t)p * C + (size_t)col * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v.v[i];
+  }
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[row * C + col * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < rows; ++r) a += (double)sm[r * C + c];
+    bpart[(size_t)blockIdx.x * C + c] = (float)a;
+  }
+}
+
+bool conv_tc_wgrad_supported(int H, int W, int Cin, int Cout, int stride) {
+  if (Cin % 64 || Cout % 64) return false;
+  if (Cout > 256 && Cout % 256) return false;
+  if (Cout < 256 && (Cout & (Cout - 1))) return false;  // 64, 128, 256
+  if (stride == 2 && ((H | W) & 1)) return false;
+  const int OW = (W - 1) / stride + 1, OH = (H - 1) / stride + 1;
+  int tw, th, tn;
+  return tile_geom(OW, OH, &tw, &th, &tn, WG_PIX);
+}
+
+WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int stride) {
+  WgradTcPlan pl;
+  const int OW = (W - 1) / stride + 1, OH = (H - 1) / stride + 1;
+  int tw, th, tn;
+  tile_geom(OW, OH, &tw, &th, &tn, WG_PIX);
+  pl.bn = Cout < 256 ? Cout : 256;
+  const int units = 9 * (Cin / 64), rbs = (units + 1) / 2;
+  int slots = 512 / pl.bn;
+  const int nb = pl.bn / 64;
+  const int budget = (96 * 1024 - nb * (int)WG_BOX) / (2 * (int)WG_BOX);  // keep a stage under ~96 KB
+  if (slots > budget) slots = budget;
+  if (slots > rbs) slots = rbs;
+  if (slots < 1) slots = 1;
+  // balance the row blocks over the groups (e.g. 9 blocks -> 5 + 4 rather than 8 + 1)
+  const int groups = (rbs + slots - 1) / slots;
+  slots = (rbs + groups - 1) / groups;
+  pl.slots = slots;
+  pl.groups = groups;
+  pl.tiles_total = (OW / tw) * (OH / th) * ((B + tn - 1) / tn);
+  const int ctas_fixed = groups * (Cout / pl.bn);
+  int splits = (num_sms() + ctas_fixed - 1) / ctas_fixed;
+  if (splits > pl.tiles_total) splits = pl.tiles_total;
+  if (splits < 1) splits = 1;
+  pl.tiles_per_split = (pl.tiles_total + splits - 1) / splits;
+  pl.splits = (pl.tiles_total + pl.tiles_per_split - 1) / pl.tiles_per_split;
+  const long long npix = (long long)B * OH * OW;
+  pl.bias_pix_per_chunk = 4096;
+  pl.bias_chunks = (int)((npix + pl.bias_pix_per_chunk - 1) / pl.bias_pix_per_chunk);
+  pl.part_bytes = align_up((size_t)pl.splits * 9 * Cin * Cout * sizeof(float), 256);
+  pl.bpart_bytes = align_up((size_t)pl.bias_chunks * Cout * sizeof(float), 256);
+  return pl;
+}
+
+int conv_tc_wgrad(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
+                  int W, int Cin, int Cout, int stride, cudaStream_t st) {
+  WgMaps maps;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  const int OW = (W - 1) / stride + 1, OH = (H - 1) / stride + 1;
+  BVAE_REQUIRE(tile_geom(OW, OH, &p.tw, &p.th, &p.tn, WG_PIX), BVAE_ERR_UNSUPPORTED, "conv_tc_wgrad: tile geometry");
+  p.tiles_w = OW / p.tw;
+  p.tiles_h = OH / p.th;
+  p.tiles_total = pl.tiles_total;
+  p.tiles_per_split = pl.tiles_per_split;
+  p.cin_chunks = Cin / 64;
+  p.units = 9 * p.cin_chunks;
+  p.slots = pl.slots;
+  p.bn = pl.bn;
+  p.B = B; p.Cin = Cin; p.Cout = Cout;
+  p.part = part;
+  const uint32_t box[4] = {64u, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+  int rc;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)OW * Cout * 2, (uint64_t)OH * OW * Cout * 2};
+    rc = make_map(&maps.dy, dy, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  if (stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    rc = make_map(&maps.x[0], x, 4, dims, strides, box, 128);
+    if (rc) return rc;
+    for (int t = 0; t < 9; ++t) p.taps[t] = TcTap{0, (int8_t)(t / 3 - 1), (int8_t)(t % 3 - 1), (int8_t)t};
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        const char* base = reinterpret_cast<const char*>(x) + ((size_t)ph * W + pw) * Cin * 2;
+        rc = make_map(&maps.x[ph * 2 + pw], base, 4, dims, strides, box, 128);
+        if (rc) return rc;
+      }
+    for (int t = 0; t < 9; ++t) {
+      const int r = t / 3, s = t % 3;
+      const int ph = (r == 1) ? 0 : 1, di = (r == 0) ? -1 : 0;
+      const int pw = (s == 1) ? 0 : 1, dj = (s == 0) ? -1 : 0;
+      p.taps[t] = TcTap{(int8_t)(ph * 2 + pw), (int8_t)di, (int8_t)dj, (int8_t)t};
+    }
+  }
+  const uint32_t stage_bytes = (uint32_t)(p.bn / 64 + 2 * p.slots) * WG_BOX;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < p.slots * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_tc_wgrad: cudaFuncSetAttribute");
+    configured = smem;
+  }
+  dim3 grid(pl.groups, Cout / p.bn, pl.splits);
+  conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p);
+  BVAE_LAUNCH_CHECK("conv_wgrad_tc");
+  if (bpart) {
+    const int cv = Cout / 8;
+    const int rows = 256 / cv > 0 ? 256 / cv : 1;
+    const int threads = (cv * rows + 31) / 32 * 32;
+    const long long npix = (long long)B * OH * OW;
+    colsum_bf16_kernel<<<pl.bias_chunks, threads, (size_t)rows * Cout * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), bpart, npix, Cout, cv, rows, pl.bias_pix_per_chunk);
+    BVAE_LAUNCH_CHECK("colsum_bf16");
+  }
+  return BVAE_OK;
+}
+
+}  // namespace bvae
