@@ -295,6 +295,13 @@ def cuda_main(args):
                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
         roofline.update({"ms_per_call": per_call_ms, "launches_per_call": a["launches"] / a["calls"],
                          "share_of_profiled_step": a["ms"] / total_ms})
+        if rank == 0:
+            print(f"# per-op CUDA-event profile: {total_ms / args.steps:.3f} ms/step inside C-ABI calls", file=sys.stderr)
+            for t, v in ranked:
+                print(f"#  {t:42s} {v['ms'] / args.steps:8.4f} ms/step  {100 * v['ms'] / total_ms:5.1f}%  "
+                      f"launches/call {v['launches'] / v['calls']:.0f}  "
+                      f"{(v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['flops'] else 0:8.1f} TFLOP/s  "
+                      f"{(v['bytes'] / (v['ms'] * 1e-3) / 1e9) if v['bytes'] else 0:8.1f} GB/s", file=sys.stderr)
         for t, v in ranked[:12]:
             top.append({"op": t, "ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_ms,
                         "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else None,
