@@ -192,7 +192,7 @@ def cuda_main(args):
 
     from bvae_rt import lib, profiler
     from bvae_rt.data import synthetic_batch
-    from bvae_rt.engine import TrainEngine
+    from bvae_rt.engine import GraphedTrainStep, TrainEngine
     from models.beta_vae import BetaVAE
     from utils.brain_tumor_utils.config_parser import freeze
     lib.load()
@@ -212,7 +212,7 @@ def cuda_main(args):
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     scal = torch.zeros(4, device=dev)
 
-    def train_step(x):
+    def train_step_eager(x):
         engine.zero_grad()
         eps = torch.randn(batch, latent, device=dev, generator=gen)
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -220,6 +220,12 @@ def cuda_main(args):
         out["total"].backward()
         engine.step()
         return out
+
+    graphed = None if args.no_graph else GraphedTrainStep(engine, (batch, 1, size, size), seed=7 + rank)
+
+    def train_step(x):
+        # the whole step (zero_grad .. Adam) is one CUDA-graph replay; x may be a device or pinned host tensor
+        return graphed(x, **LOSS_KW) if graphed is not None else train_step_eager(x)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -251,6 +257,8 @@ def cuda_main(args):
     with ClockSampler(local) as clk:
         ms = timed(lambda i: train_step(xs[i % n_batches]), args.steps)
     launches = lib.query("bvae_launch_count") - l0
+    if graphed is not None:
+        launches = graphed.launches_per_step * args.steps    # kernels inside the replayed graph
     value = world * batch * args.steps / (ms / 1e3)
 
     # ---- (2) end to end through the public API with host buffers
@@ -259,8 +267,11 @@ def cuda_main(args):
     host_out = torch.empty(4, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        xdev.copy_(host[i % n_batches], non_blocking=True)           # H2D of this step's input
-        out = train_step(xdev)
+        if graphed is not None:
+            out = train_step(host[i % n_batches])                    # H2D of this step's input (into the graph's buffer)
+        else:
+            xdev.copy_(host[i % n_batches], non_blocking=True)
+            out = train_step(xdev)
         scal[0], scal[1], scal[2], scal[3] = out["total"].detach(), out["recon"].detach(), out["kl_mean"].detach(), \
             out["recon_ffl"]
         host_out.copy_(scal, non_blocking=True)                      # D2H of the step's loss scalars
@@ -275,7 +286,7 @@ def cuda_main(args):
     # ---- (3) per-op CUDA-event pass for the roofline of the dominant kernel
     prof = profiler.start()
     for i in range(args.steps):
-        train_step(xs[i % n_batches])
+        train_step_eager(xs[i % n_batches])
     agg = profiler.stop().summary()
     peaks = measured_peaks()
     roofline, top = None, []
@@ -326,6 +337,7 @@ def cuda_main(args):
                        "image_size": size, "per_gpu_batch": batch, "global_batch": batch * world,
                        "objective": "capacity C=30 gamma=1, FFL 0.5 (torch.fft), mse",
                        "parallelism": f"dp{world}",
+                       "launch": "eager" if graphed is None else "whole step captured in one CUDA graph",
                        "l2": f"no explicit flush: a step streams ~{act_mb:.0f} MB of activations plus 8 rotating "
                              f"input batches, above the 126 MB L2"},
             "clocks": clk.result(),
@@ -349,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: training.batch_size of the config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)

@@ -98,6 +98,7 @@ class TrainEngine:
         self._works = []
         self._bucket_of = {n: i for i, b in enumerate(self.bucket_names) for n in b}
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._hyper = torch.zeros(4, dtype=torch.float32, device=dev)   # lr, 1-b1^t, sqrt(1-b2^t)
         self._ws = torch.empty(query("bvae_adam_workspace", self.numel), dtype=torch.uint8, device=dev)
         self._hooks = []
         arena = ops.GradArena()
@@ -152,26 +153,44 @@ class TrainEngine:
         self._works = []
 
     # ------------------------------------------------------------------ the step
-    def step(self):
-        """Global-norm clip + Adam over the flat buffers.  Gradients are SUMS over ranks at this
-        point; the 1/world average is folded into the kernel's grad_scale."""
-        self.finish_reduce()
+    def _zero_unused(self):
         # parameters whose gradient never arrived (unused) must not contribute stale data
         for bi, left in enumerate(self._pending):
             if left > 0:
                 for n in self.bucket_names[bi]:
                     if self._named[n].grad is None:
                         self.slots[n][2].zero_()
+
+    def advance(self):
+        """Host side of a step: bump the step counter and publish this step's scalars (lr and the
+        Adam bias corrections) to the device buffer the graph-safe kernels read."""
         self.step_count += 1
+        b1, b2 = self.betas
+        self._hyper.copy_(torch.tensor([self.lr, 1.0 - b1 ** self.step_count,
+                                        math.sqrt(1.0 - b2 ** self.step_count), 0.0], dtype=torch.float32))
+
+    def step(self, from_device_scalars: bool = False):
+        """Global-norm clip + Adam over the flat buffers.  Gradients are SUMS over ranks at this
+        point; the 1/world average is folded into the kernel's grad_scale.
+        ``from_device_scalars``: launch only (lr / bias corrections come from the device buffer that
+        ``advance()`` fills) -- the form a captured CUDA graph replays."""
+        self.finish_reduce()
+        self._zero_unused()
         st = torch.cuda.current_stream().cuda_stream
         n = self.numel
         if self.clip > 0:
             call("bvae_grad_sumsq", self.flat_g.data_ptr(), n, self._sumsq.data_ptr(), self._ws.data_ptr(),
                  self._ws.numel(), st)
-        call("bvae_adam_clip_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
-             self.flat_v.data_ptr(), n, self._sumsq.data_ptr() if self.clip > 0 else None, 1.0 / self.world,
-             self.clip, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-             1 if self.decoupled_wd else 0, self.step_count, st)
+        sumsq = self._sumsq.data_ptr() if self.clip > 0 else None
+        if from_device_scalars:
+            call("bvae_adam_clip_step_dev", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                 self.flat_v.data_ptr(), n, sumsq, 1.0 / self.world, self.clip, self._hyper.data_ptr(),
+                 self.betas[0], self.betas[1], self.eps, self.weight_decay, 1 if self.decoupled_wd else 0, st)
+        else:
+            self.step_count += 1
+            call("bvae_adam_clip_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                 self.flat_v.data_ptr(), n, sumsq, 1.0 / self.world, self.clip, self.lr, self.betas[0],
+                 self.betas[1], self.eps, self.weight_decay, 1 if self.decoupled_wd else 0, self.step_count, st)
         if hasattr(self.model, "invalidate_packs"):
             self.model.invalidate_packs()                      # parameters changed through raw pointers
 
@@ -220,6 +239,78 @@ class TrainEngine:
         for h in self._hooks:
             h.remove()
         ops.set_grad_arena(None)
+
+
+class GraphedTrainStep:
+    """One whole training step -- zero_grad, ``BetaVAE.loss`` under autocast, backward, bucketed
+    gradient all-reduce, clip + Adam -- captured once into a CUDA graph and replayed.
+
+    The reference's loop issues the same sequence from Python every step
+    (src/training/train.py:313-333); at the configured batch of 32 the B200 finishes the kernels
+    faster than Python can enqueue them, so the launch sequence is recorded once.  Inputs live
+    in static device buffers (``x``, ``eps``); per-step host scalars (lr, Adam bias corrections)
+    are read from a device buffer; anything baked into kernel arguments (beta, capacity,
+    free_bits -- they change per epoch) triggers a re-capture when it changes.
+
+    The first ``eager_steps`` calls run un-captured (they are real steps and warm up lazy
+    initialisation: cuFFT plans, smem attributes); the next call captures, and every call from
+    then on replays.  Returns ``model.loss``'s dictionary; its tensors are the graph's static
+    outputs and are overwritten by the next call."""
+
+    def __init__(self, engine: "TrainEngine", batch_shape, autocast_dtype=torch.bfloat16, eager_steps: int = 2,
+                 seed: int = 0):
+        self.engine, self.model = engine, engine.model
+        dev = engine.device
+        self.x = torch.zeros(batch_shape, dtype=torch.float32, device=dev)
+        self.eps = torch.zeros(batch_shape[0], self.model.latent_dim, dtype=torch.float32, device=dev)
+        self.autocast_dtype = autocast_dtype
+        self.eager_steps = eager_steps
+        self.calls = 0
+        self.graph = None
+        self.out = None
+        self._kw = None
+        self.launches_per_step = None
+        self._gen = torch.Generator(device=dev).manual_seed(seed)
+
+    def _body(self, kw):
+        self.engine.zero_grad()
+        if self.autocast_dtype is None:
+            out = self.model.loss(self.x, eps=self.eps, **kw)
+        else:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                out = self.model.loss(self.x, eps=self.eps, **kw)
+        out["total"].backward()
+        self.engine.step(from_device_scalars=True)
+        # hand back plain tensors: a live autograd graph would pin this iteration's AccumulateGrad
+        # nodes (and their stream) and break the capture that follows the eager steps
+        return {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+
+    def _capture(self, kw):
+        from .lib import query
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = query("bvae_launch_count")
+        self.engine.zero_grad()
+        with torch.cuda.graph(g):
+            out = self._body(kw)
+        self.launches_per_step = query("bvae_launch_count") - n0
+        self.graph, self.out, self._kw = g, out, dict(kw)
+
+    def __call__(self, x, eps=None, **kw):
+        self.x.copy_(x, non_blocking=True)
+        if eps is None:
+            self.eps.normal_(generator=self._gen)
+        else:
+            self.eps.copy_(eps, non_blocking=True)
+        self.engine.advance()
+        self.calls += 1
+        if self.calls <= self.eager_steps:
+            return self._body(kw)
+        if self.graph is None or kw != self._kw:
+            self._capture(kw)
+        self.graph.replay()
+        self.model.invalidate_packs()      # weight packs inside the graph pool are one step old for eager callers
+        return self.out
 
 
 def cosine_lr(base_lr: float, epoch: int, t_max: int, eta_min: float = 0.0) -> float:

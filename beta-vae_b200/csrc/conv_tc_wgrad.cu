@@ -226,7 +226,13 @@ WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int strid
   pl.tiles_per_split = (pl.tiles_total + splits - 1) / splits;
   pl.splits = (pl.tiles_total + pl.tiles_per_split - 1) / pl.tiles_per_split;
   const long long npix = (long long)B * OH * OW;
-  pl.bias_pix_per_chunk = 4096;
+  {
+    // enough chunks for ~4 CTAs per SM; a chunk is at least 4 passes of the CTA's pixel rows
+    const int cv = Cout / 8, rows = 256 / cv > 0 ? 256 / cv : 1;
+    long long per = (npix + 4LL * num_sms() - 1) / (4LL * num_sms());
+    if (per < 4LL * rows) per = 4LL * rows;
+    pl.bias_pix_per_chunk = (int)per;
+  }
   pl.bias_chunks = (int)((npix + pl.bias_pix_per_chunk - 1) / pl.bias_pix_per_chunk);
   pl.part_bytes = align_up((size_t)pl.splits * 9 * Cin * Cout * sizeof(float), 256);
   pl.bpart_bytes = align_up((size_t)pl.bias_chunks * Cout * sizeof(float), 256);

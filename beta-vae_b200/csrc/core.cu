@@ -151,7 +151,13 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const double* __restri
 __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 size_t n, const float* __restrict__ sumsq, float grad_scale, float max_norm, float lr, float b1,
-                float b2, float eps, float wd, int decoupled, float bc1, float bc2_sqrt) {
+                float b2, float eps, float wd, int decoupled, float bc1, float bc2_sqrt,
+                const float* __restrict__ hyper) {
+  if (hyper) {  // per-step scalars from device memory (CUDA-graph replays): lr, 1-b1^t, sqrt(1-b2^t)
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2_sqrt = hyper[2];
+  }
   float clip = grad_scale;
   if (max_norm > 0.f && sumsq) {
     const float total = sqrtf(sumsq[0]) * grad_scale;
@@ -278,7 +284,18 @@ extern "C" int bvae_adam_clip_step(float* p, const float* g, float* m, float* v,
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for((long long)n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, sumsq, grad_scale, max_norm, lr,
                                                                     beta1, beta2, eps, weight_decay, decoupled_wd,
-                                                                    (float)bc1, (float)sqrt(bc2));
+                                                                    (float)bc1, (float)sqrt(bc2), nullptr);
   BVAE_LAUNCH_CHECK("adam_clip_step");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_adam_clip_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
+                                       float grad_scale, float max_norm, const float* hyper, float beta1, float beta2,
+                                       float eps, float weight_decay, int decoupled_wd, bvae_stream_t stream) {
+  BVAE_REQUIRE(p && g && m && v && hyper && n > 0, BVAE_ERR_ARG, "adam_clip_step_dev: bad argument");
+  adam_kernel<<<grid_for((long long)n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, sumsq, grad_scale, max_norm, 0.f,
+                                                                    beta1, beta2, eps, weight_decay, decoupled_wd,
+                                                                    1.f, 1.f, hyper);
+  BVAE_LAUNCH_CHECK("adam_clip_step_dev");
   return BVAE_OK;
 }

@@ -182,6 +182,11 @@ int bvae_grad_sumsq(const float* g, size_t n, float* sumsq_out, void* ws, size_t
 int bvae_adam_clip_step(float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
                         float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
                         float weight_decay, int decoupled_wd, int step, bvae_stream_t stream);
+/* Same step with the per-step scalars read from DEVICE memory, so one captured CUDA graph can be
+ * replayed for every step: hyper[0] = lr, hyper[1] = 1 - beta1^t, hyper[2] = sqrt(1 - beta2^t). */
+int bvae_adam_clip_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
+                            float grad_scale, float max_norm, const float* hyper, float beta1, float beta2,
+                            float eps, float weight_decay, int decoupled_wd, bvae_stream_t stream);
 
 /* NCHW fp32 -> NHWC act dtype (RGB input path, data.grayscale: false) and back. */
 int bvae_nchw_to_nhwc(const float* x, void* y, int B, int C, int H, int W, int dtype, bvae_stream_t stream);

@@ -186,3 +186,43 @@ def test_training_trajectory_matches_oracle_fp32():
     # the sharp check
     for k, v in m.state_dict().items():
         assert rel_err(v, sd[k]) <= 5e-2, k
+
+
+def test_graphed_train_step_matches_eager_engine():
+    """The CUDA-graph replay of the whole step (bvae_rt.engine.GraphedTrainStep) follows the
+    same trajectory as the engine driven kernel by kernel, and as the oracle + torch Adam."""
+    from oracle import beta_vae_oracle as O
+    from bvae_rt.engine import GraphedTrainStep, TrainEngine
+    import cfgs
+    cfg = cfgs.small(loss__use_ffl=True, loss__ffl_weight=0.5)
+    spec = O.spec_from_config(cfgs.ns(cfg))
+    torch.manual_seed(3)
+    ref = build_model(cfg, None, "fp32")
+    state = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in state.items()}
+    opt_o = torch.optim.Adam(list(sd.values()), lr=2e-3)
+    kw = dict(beta=1.0, capacity=3.0, free_bits=0.0, capacity_weight=1.0)
+    g = torch.Generator().manual_seed(5)
+    data = [(torch.rand(4, 1, 32, 32, generator=g), torch.randn(4, 8, generator=g)) for _ in range(6)]
+
+    m = build_model(cfg, state, "fp32")
+    eng = TrainEngine(m, lr=2e-3, clip=3.0)
+    step = GraphedTrainStep(eng, (4, 1, 32, 32), autocast_dtype=None, eager_steps=2)
+    losses = []
+    try:
+        for x, eps in data:
+            out = step(x.cuda(), eps=eps.cuda(), **kw)
+            losses.append(float(out["total"]))
+        assert step.graph is not None and step.launches_per_step > 10
+        assert eng.step_count == len(data)
+    finally:
+        eng.close()
+    for (x, eps), lg in zip(data, losses):
+        opt_o.zero_grad(set_to_none=True)
+        lo = O.loss(sd, spec, x, eps, **kw)["total"]
+        lo.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), 3.0)
+        opt_o.step()
+        assert abs(lg - float(lo)) <= 2e-5 * abs(float(lo)), (lg, float(lo))
+    for k, v in m.state_dict().items():
+        assert rel_err(v, sd[k]) <= 5e-2, k
