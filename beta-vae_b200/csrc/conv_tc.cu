@@ -216,6 +216,7 @@ static int make_weight_map(CUtensorMap* m, const void* wp, int K, int N, int kc,
 
 int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
                   int stride, cudaStream_t st) {
+  if (stride == 1 && conv_halo_supported(H, W, Cin, Cout)) return conv_halo_launch(x, wp, bias, y, B, H, W, Cin, Cout, 0, st);
   TcMaps maps;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -264,6 +265,7 @@ int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int
 
 int conv_tc_dgrad(const void* dy, const void* wpt, void* dx, int B, int H, int W, int Cin, int Cout, int stride,
                   cudaStream_t st) {
+  if (stride == 1 && conv_halo_supported(H, W, Cout, Cin)) return conv_halo_launch(dy, wpt, nullptr, dx, B, H, W, Cout, Cin, 1, st);
   TcMaps maps;
   TcParams p;
   memset(&p, 0, sizeof(p));

@@ -41,6 +41,11 @@ int conv_tc_fprop(const void* x, const void* wp_nk, const float* bias, void* y, 
 int conv_tc_dgrad(const void* dy, const void* wpt_nk, void* dx, int B, int H, int W, int Cin, int Cout, int stride,
                   cudaStream_t st);
 
+// ---- stride-1 halo kernel (conv_tc_halo.cu): persistent, one shared-memory halo per tile, weights resident ----
+bool conv_halo_supported(int H, int W, int K, int N);
+int conv_halo_launch(const void* src, const void* wp_nk, const float* bias, void* dst, int B, int H, int W, int K, int N,
+                     int dgrad, cudaStream_t st);
+
 // ---- wgrad (conv_tc_wgrad.cu) ----
 struct WgradTcPlan {
   int bn, slots, groups;           // co tile, accumulator slots per CTA, row-block groups

@@ -1,0 +1,376 @@
+// Stride-1 3x3 convolution (fprop and dgrad) on tcgen05: persistent implicit GEMM whose A operand
+// is ONE shared-memory halo per (tile, 64-channel chunk), read nine times as shifted windows.
+// (reference op: nn.Conv2d(3x3, stride 1, pad 1) at src/models/beta_vae.py:54 -- the decoder convs,
+//  86 % of the model's FLOPs -- and convolution_backward's input gradient for it.)
+//
+// Why: the tap-per-TMA-load formulation (conv_tc.cu) re-reads every input pixel nine times from L2
+// and re-fetches the weights for every tile.  At N = 64..128 output channels a 128-pixel tile then
+// needs 110-190 B of shared-memory fill per tensor-core cycle while L2 delivers roughly 35-60 B
+// per SM-cycle, so the tensor pipe idles.  Here
+//   * a tile is 16 x 8 output pixels; its (18 x 10 pixel) x 64-channel input halo arrives with one
+//     4-D TMA box (23 KB, out-of-image rows/columns zero-filled = the conv's padding) in the
+//     128B-swizzled K-major layout.  Tap (di, dj) is the same buffer read through a descriptor whose
+//     start address is shifted by ((di+1)*10 + (dj+1)) pixel rows and whose 8-row group stride is one
+//     halo row (1280 B): the UMMA unit swizzles on absolute address bits, so windows that are not
+//     aligned to the 1024-B swizzle atom are read correctly (dev/halo_desc_probe.cu is the probe
+//     that established this on B200).  Input traffic drops 6.4x.
+//   * CTAs are persistent (one per SM, static round-robin over work units) and keep the whole
+//     [9][bn][K] weight slab resident in shared memory when it fits (K*bn <= 8192: the 64/128-channel
+//     layers); otherwise weights stream through a second ring, shared by TM = 2 pixel tiles.
+//   * accumulators are double-buffered in TMEM, so the epilogue of unit i (TMEM -> registers ->
+//     +bias -> bf16 -> global) overlaps the MMAs of unit i+1.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace bvae {
+
+static constexpr int HL_THREADS = 192;
+static constexpr int HL_TH = 16, HL_TW = 8;                      // output tile
+static constexpr int HL_HW = HL_TW + 2, HL_HH = HL_TH + 2;       // halo
+static constexpr uint32_t HL_ROW = 128;                          // one pixel = 64 bf16 channels
+static constexpr uint32_t HL_HALO_BYTES = HL_HH * HL_HW * HL_ROW;  // 23040
+static constexpr uint32_t HL_HALO_SLOT = 24576;                  // padded to the 1024-B swizzle atom
+static constexpr uint32_t HL_GROUP_STRIDE = HL_HW * HL_ROW;      // 1280: next tile row in the halo
+
+struct HaloParams {
+  int dgrad;               // 1: flipped taps (weight tap 8-j with halo window j)
+  int kchunks;             // K / 64
+  int bn, n_tiles;         // output channels per unit, N / bn
+  int tm;                  // pixel tiles per unit (share every weight stage)
+  int tiles_w, tiles_h, m_tiles;  // tiles per image row / column, total pixel tiles
+  int m_groups, units;
+  int B, H, W, N;
+  int resident;            // weights resident in shared memory
+  int sa, sb;              // ring depths
+  int nbuf, tmem_cols;     // accumulator buffers in TMEM
+  uint32_t a_off, b_off, bar_off;
+  __nv_bfloat16* dst;
+  const float* bias;
+};
+
+struct HaloMaps {
+  CUtensorMap x;
+  CUtensorMap w;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major SW128 descriptor with an explicit 8-row-group stride (halo windows: 1280 B)
+__device__ __forceinline__ uint64_t kmajor_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= 1ull << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
+// Window j = (r, s) of the halo starts ((r * 10) + s) pixel rows into the buffer.  fprop uses weight tap j with
+// window j; dgrad (flipped kernel) uses weight tap 8 - j with window j -- the producer stores tap `wtap(j)` in
+// weight slot j, so the MMA loop is identical for both and fully unrolled with constant offsets.
+template <int BN, bool RESIDENT>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+    conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem + p.a_off;
+  uint8_t* b_base = smem + p.b_off;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* a_empty = a_full + p.sa;
+  uint64_t* b_full = a_empty + p.sa;
+  uint64_t* b_empty = b_full + p.sb;
+  uint64_t* acc_full = b_empty + p.sb;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_res = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
+  float* bias_sm = reinterpret_cast<float*>(smem + p.bar_off + 256);  // [N] (zeros when there is no bias)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_slot_bytes = (uint32_t)p.tm * HL_HALO_SLOT;
+  constexpr uint32_t b_tap_bytes = (uint32_t)BN * HL_ROW;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.sa; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.sb; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_init(b_res, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.N; i += HL_THREADS) bias_sm[i] = p.bias ? p.bias[i] : 0.f;
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.x);
+      tma_prefetch_desc(&maps.w);
+      if (RESIDENT) {
+        // every unit of this CTA has the same n-tile (gridDim.x is a multiple of n_tiles)
+        const int n0 = (blockIdx.x % p.n_tiles) * BN;
+        mbar_expect_tx(b_res, 9u * p.kchunks * b_tap_bytes);
+        for (int c = 0; c < p.kchunks; ++c)
+          for (int j = 0; j < 9; ++j)
+            tma_load_3d(&maps.w, b_res, b_base + (size_t)(c * 9 + j) * b_tap_bytes, c * 64, n0, p.dgrad ? 8 - j : j);
+      }
+      uint32_t ia = 0, ib = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int nt = u % p.n_tiles, mg = u / p.n_tiles;
+        const int n0 = nt * BN;
+        for (int c = 0; c < p.kchunks; ++c, ++ia) {
+          const uint32_t sa = ia % p.sa;
+          mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
+          int live = 0;
+          for (int m = 0; m < p.tm; ++m) live += (mg * p.tm + m < p.m_tiles) ? 1 : 0;
+          mbar_expect_tx(&a_full[sa], (uint32_t)live * HL_HALO_BYTES);
+          for (int m = 0; m < live; ++m) {
+            int mt = mg * p.tm + m;
+            const int w0 = (mt % p.tiles_w) * HL_TW;
+            mt /= p.tiles_w;
+            const int h0 = (mt % p.tiles_h) * HL_TH;
+            const int b = mt / p.tiles_h;
+            tma_load_4d(&maps.x, &a_full[sa], a_ring + (size_t)sa * a_slot_bytes + (size_t)m * HL_HALO_SLOT, c * 64, w0 - 1,
+                        h0 - 1, b);
+          }
+          if (!RESIDENT) {
+#pragma unroll 1
+            for (int j = 0; j < 9; ++j, ++ib) {
+              const uint32_t sb = ib % p.sb;
+              mbar_wait(&b_empty[sb], ((ib / p.sb) & 1u) ^ 1u);
+              mbar_expect_tx(&b_full[sb], b_tap_bytes);
+              tma_load_3d(&maps.w, &b_full[sb], b_base + (size_t)sb * b_tap_bytes, c * 64, n0, p.dgrad ? 8 - j : j);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread; the tap / k loops are unrolled with constant descriptor offsets) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc =
+          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      if (RESIDENT) {
+        mbar_wait(b_res, 0);
+        tc_fence_after();
+      }
+      uint32_t ia = 0, ib = 0, iu = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+        const int mg = u / p.n_tiles;
+        const uint32_t buf = iu % p.nbuf;
+        mbar_wait(&acc_empty[buf], ((iu / p.nbuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * (uint32_t)(p.tm * BN);
+        const int live = (mg * p.tm + 1 < p.m_tiles && p.tm == 2) ? 2 : 1;
+        for (int c = 0; c < p.kchunks; ++c, ++ia) {
+          const uint32_t sa = ia % p.sa;
+          mbar_wait(&a_full[sa], (ia / p.sa) & 1u);
+          tc_fence_after();
+          const uint64_t a_desc0 = kmajor_desc_sbo(smem_u32(a_ring + (size_t)sa * a_slot_bytes), HL_GROUP_STRIDE);
+          const uint64_t b_desc_res = kmajor_desc(smem_u32(b_base + (size_t)c * 9 * b_tap_bytes), HL_ROW);
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            uint64_t b_desc;
+            uint32_t sb = 0;
+            if (RESIDENT) {
+              b_desc = b_desc_res + (uint64_t)((j * b_tap_bytes) >> 4);
+            } else {
+              sb = ib % p.sb;
+              mbar_wait(&b_full[sb], (ib / p.sb) & 1u);
+              tc_fence_after();
+              b_desc = kmajor_desc(smem_u32(b_base + (size_t)sb * b_tap_bytes), HL_ROW);
+              ++ib;
+            }
+            constexpr uint32_t dummy = 0;
+            (void)dummy;
+            const uint32_t win = (uint32_t)((j / 3) * HL_HW + (j % 3)) * HL_ROW;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(acc, a_desc0 + (uint64_t)((win + k * 32) >> 4), b_desc + (uint64_t)(k * 2), idesc,
+                        (j | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+            if (live == 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(acc + BN, a_desc0 + (uint64_t)((HL_HALO_SLOT + win + k * 32) >> 4), b_desc + (uint64_t)(k * 2),
+                          idesc, (j | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+            }
+            if (!RESIDENT) umma_commit(&b_empty[sb]);
+          }
+          umma_commit(&a_empty[sa]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;            // pixel inside the 16x8 tile
+    const int hl = r / HL_TW, wl = r % HL_TW;
+    uint32_t iu = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      const int nt = u % p.n_tiles, mg = u / p.n_tiles;
+      const int n0 = nt * BN;
+      const uint32_t buf = iu % p.nbuf;
+      mbar_wait(&acc_full[buf], (iu / p.nbuf) & 1u);
+      tc_fence_after();
+      for (int m = 0; m < p.tm; ++m) {
+        int mt = mg * p.tm + m;
+        if (mt >= p.m_tiles) break;
+        const int w0 = (mt % p.tiles_w) * HL_TW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * HL_TH;
+        const int b = mt / p.tiles_h;
+        __nv_bfloat16* out = p.dst + (((size_t)b * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl)) * p.N + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.tm * BN) + (uint32_t)(m * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+          const float4* bq = reinterpret_cast<const float4*>(bias_sm + n0 + c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0 = bq[2 * g], b1 = bq[2 * g + 1];
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float f0 = __uint_as_float(v[g * 8 + 2 * e]) + bb[2 * e];
+              const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + bb[2 * e + 1];
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static constexpr size_t HL_SMEM_MAX = 227 * 1024;
+
+bool conv_halo_supported(int H, int W, int K, int N) {
+  if (getenv("BVAE_CONV_NO_HALO")) return false;
+  return H % HL_TH == 0 && W % HL_TW == 0 && K % 64 == 0 && N % 64 == 0 && (N <= 256 ? (N & (N - 1)) == 0 : N % 256 == 0);
+}
+
+int conv_halo_launch(const void* src, const void* wp, const float* bias, void* dst, int B, int H, int W, int K, int N,
+                     int dgrad, cudaStream_t st) {
+  HaloMaps maps;
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.dgrad = dgrad ? 1 : 0;
+  p.kchunks = K / 64;
+  p.tiles_w = W / HL_TW;
+  p.tiles_h = H / HL_TH;
+  p.m_tiles = p.tiles_w * p.tiles_h * B;
+  p.B = B; p.H = H; p.W = W; p.N = N;
+  p.dst = reinterpret_cast<__nv_bfloat16*>(dst);
+  p.bias = bias;
+  const int sms = num_sms();
+  const size_t bar_bytes = 256 + (size_t)N * sizeof(float) + 64;  // mbarriers + bias[N]
+  // resident weights: the whole [9][bn][K] slab plus at least two halo slots must fit
+  int bn_res = 0;
+  for (int bn = (N < 256 ? N : 256); bn >= 64; bn >>= 1) {
+    if (N % bn) continue;
+    if ((size_t)9 * K * bn * 2 + 2 * HL_HALO_SLOT + bar_bytes + 1024 <= HL_SMEM_MAX) {
+      bn_res = bn;
+      break;
+    }
+  }
+  size_t smem;
+  if (bn_res) {
+    p.resident = 1;
+    p.bn = bn_res;
+    p.tm = 1;
+    p.sb = 0;
+    const size_t wbytes = (size_t)9 * K * p.bn * 2;
+    int sa = (int)((HL_SMEM_MAX - 1024 - bar_bytes - wbytes) / HL_HALO_SLOT);
+    p.sa = sa > 4 ? 4 : sa;
+    p.b_off = 0;
+    p.a_off = (uint32_t)wbytes;  // multiple of 1024 (bn*128*9*kchunks)
+    p.bar_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;
+    smem = 1024 + p.bar_off + bar_bytes;
+  } else {
+    p.resident = 0;
+    p.bn = N >= 128 ? 128 : 64;
+    const int units1 = p.m_tiles * (N / p.bn);
+    p.tm = (units1 / 2 >= (sms * 4) / 5) ? 2 : 1;
+    p.sa = p.tm == 2 ? 2 : 3;
+    const size_t a_bytes = (size_t)p.sa * p.tm * HL_HALO_SLOT;
+    int sb = (int)((HL_SMEM_MAX - 1024 - bar_bytes - a_bytes) / ((size_t)p.bn * HL_ROW));
+    p.sb = sb > 8 ? 8 : sb;
+    p.a_off = 0;
+    p.b_off = (uint32_t)a_bytes;
+    p.bar_off = p.b_off + (uint32_t)p.sb * p.bn * HL_ROW;
+    smem = 1024 + p.bar_off + bar_bytes;
+  }
+  p.n_tiles = N / p.bn;
+  p.m_groups = (p.m_tiles + p.tm - 1) / p.tm;
+  p.units = p.m_groups * p.n_tiles;
+  p.nbuf = (2 * p.tm * p.bn <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < p.nbuf * p.tm * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  BVAE_REQUIRE(smem <= HL_SMEM_MAX, BVAE_ERR_UNSUPPORTED, "conv_halo: shared memory plan %zu too large", smem);
+
+  {
+    const uint64_t dims[4] = {(uint64_t)K, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)K * 2, (uint64_t)W * K * 2, (uint64_t)H * W * K * 2};
+    const uint32_t box[4] = {64u, (uint32_t)HL_HW, (uint32_t)HL_HH, 1u};
+    int rc = make_map(&maps.x, src, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 9};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * N * 2};
+    const uint32_t box[3] = {64u, (uint32_t)p.bn, 1u};
+    int rc = make_map(&maps.w, wp, 3, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  int grid = p.units < sms ? p.units : sms;
+  if (p.resident) {
+    // every CTA must keep one n-tile for all its units: grid a multiple of n_tiles
+    grid = grid / p.n_tiles * p.n_tiles;
+    if (grid < p.n_tiles) grid = p.n_tiles;
+  }
+  void (*kern)(const HaloMaps, const HaloParams) = nullptr;
+  if (p.resident) kern = p.bn == 64 ? conv_halo_tc_kernel<64, true> : (p.bn == 128 ? conv_halo_tc_kernel<128, true> : conv_halo_tc_kernel<256, true>);
+  else            kern = p.bn == 64 ? conv_halo_tc_kernel<64, false> : (p.bn == 128 ? conv_halo_tc_kernel<128, false> : conv_halo_tc_kernel<256, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_halo: cudaFuncSetAttribute");
+  kern<<<grid, HL_THREADS, smem, st>>>(maps, p);
+  BVAE_LAUNCH_CHECK("conv_halo_tc");
+  return BVAE_OK;
+}
+
+}  // namespace bvae

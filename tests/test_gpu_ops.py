@@ -74,6 +74,13 @@ CONV_SHAPES = [
     (1, 128, 128, 64, 64, 1), # one image row per tile
     (2, 256, 256, 16, 16, 1), # two tiles per image row
     (5, 2, 2, 64, 64, 2),     # 1x1 output grid per sample
+    # stride-1 halo kernel (conv_tc_halo.cu): 16x8-pixel tiles, persistent CTAs
+    (8, 128, 128, 64, 64, 1),   # resident weights, ~7 tiles per CTA (double-buffered accumulators)
+    (3, 16, 8, 128, 64, 1),     # resident, two K chunks, odd tile count; dgrad: K=64 -> N=128
+    (2, 32, 16, 64, 256, 1),    # resident with two N tiles per pixel tile
+    (3, 16, 16, 512, 256, 1),   # streamed weights, 8 K chunks, TM=1
+    (40, 32, 32, 256, 128, 1),  # streamed weights shared by TM=2 pixel tiles
+    (239, 16, 8, 128, 128, 1),  # TM=2 with an odd number of tiles (last unit half empty)
 ]
 
 
