@@ -15,6 +15,8 @@
 // Split-K: every CTA owns a contiguous range of 64-pixel tiles; partial results go to the fp32
 // workspace [split][tap][ci][co] that the (deterministic) reduce kernel of conv_simt.cu sums.
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
@@ -162,6 +164,203 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------
+// Stride-1 wgrad, halo formulation (same idea as conv_tc_halo.cu): per 16x8-pixel tile ONE TMA box
+// brings the (18 x 10 pixel) x 64-channel x halo, and the nine taps are shifted MN-major windows of it
+// (start = window offset, 8-pixel atoms one halo row = 1280 B apart).  A CTA owns one
+// (64 input channels) x (64 output channels) block of dW for ALL nine taps -- five 128-row
+// accumulators in TMEM: taps (0,1) (2,3) (4,5) (6,7) (8, ones) -- and walks its share of the pixel
+// tiles (split-K over tiles).  The spare half of the fifth accumulator multiplies an all-ones A
+// block with the dy tile, i.e. it is the bias gradient: no separate column-sum pass over dy.
+// Per tile: 23 KB of x + 16 KB of dy for 40 MMAs (128x64x16) = ~30 B per tensor-core cycle.
+// ------------------------------------------------------------------------------------------
+static constexpr uint32_t WH_HALO_SLOT = 24576, WH_DY_BYTES = 16384, WH_STAGE = WH_HALO_SLOT + WH_DY_BYTES;
+static constexpr uint32_t WH_HALO_BYTES = 18 * 10 * 128, WH_ROWSTRIDE = 1280, WH_ONES_BYTES = 2560;
+
+struct WgHaloParams {
+  int cin_chunks, co_blocks;
+  int tiles_w, tiles_h, m_tiles, tiles_per_split;
+  int Cin, Cout;
+  int stages;
+  uint32_t ones_off, bar_off;
+  float* part;   // [split][9][Cin][Cout]
+  float* bpart;  // [split][Cout] or null
+};
+struct WgHaloMaps {
+  CUtensorMap x, dy;
+};
+
+__device__ __forceinline__ constexpr uint32_t wh_win(int j) { return (uint32_t)((j / 3) * 10 + (j % 3)) * 128u; }
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    conv_wgrad_halo_kernel(const __grid_constant__ WgHaloMaps maps, const WgHaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* accum_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cc = blockIdx.x % p.cin_chunks, cb = blockIdx.x / p.cin_chunks;
+  const int split = blockIdx.y;
+  const int t_beg = split * p.tiles_per_split;
+  const int t_end = min(p.m_tiles, t_beg + p.tiles_per_split);
+  const int iters = t_end - t_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  for (uint32_t i = threadIdx.x; i < WH_ONES_BYTES / 4; i += WG_THREADS)
+    reinterpret_cast<uint32_t*>(smem + p.ones_off)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+  fence_proxy_async();
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.x);
+      tma_prefetch_desc(&maps.dy);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % p.stages;
+        mbar_wait(&empty_bar[st], (((uint32_t)(it / p.stages)) & 1u) ^ 1u);
+        int tile = t_beg + it;
+        const int w0 = (tile % p.tiles_w) * 8;
+        tile /= p.tiles_w;
+        const int h0 = (tile % p.tiles_h) * 16;
+        const int b = tile / p.tiles_h;
+        uint8_t* base = smem + (size_t)st * WH_STAGE;
+        mbar_expect_tx(&full_bar[st], WH_HALO_BYTES + WH_DY_BYTES);
+        tma_load_4d(&maps.x, &full_bar[st], base, cc * 64, w0 - 1, h0 - 1, b);
+        tma_load_4d(&maps.dy, &full_bar[st], base + WH_HALO_SLOT, cb * 64, w0, h0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D fp32, A/B bf16, both MN-major, N = 64, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                 ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint64_t dconst = (1ull << 46) | (2ull << 61);
+      constexpr uint64_t a_sbo = (uint64_t)(WH_ROWSTRIDE >> 4) << 32;
+      constexpr uint64_t b_fixed = dconst | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
+      const uint32_t ones_addr = smem_u32(smem + p.ones_off);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % p.stages;
+        mbar_wait(&full_bar[st], ((uint32_t)(it / p.stages)) & 1u);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + (size_t)st * WH_STAGE);
+        const uint64_t a_lo = (uint64_t)(a0 >> 4);
+        const uint64_t b_desc0 = b_fixed | (uint64_t)((a0 + WH_HALO_SLOT) >> 4);
+        const uint32_t acc_on = it != 0 ? 1u : 0u;
+#pragma unroll
+        for (int rb = 0; rb < 5; ++rb) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const uint32_t win = wh_win(2 * rb);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint64_t lbo;
+            if (rb < 4)
+              lbo = (uint64_t)((wh_win(2 * rb + 1) - wh_win(2 * rb)) >> 4) << 16;
+            else
+              lbo = (uint64_t)((ones_addr - (a0 + win + (uint32_t)k * 2u * WH_ROWSTRIDE)) >> 4) << 16;
+            const uint64_t adesc = (dconst | a_sbo | lbo) + a_lo + (uint64_t)((win + (uint32_t)k * 2u * WH_ROWSTRIDE) >> 4);
+            umma_bf16(tmem_base + (uint32_t)(rb * 64), adesc, b_desc0 + (uint64_t)((k * 2048) >> 4), idesc,
+                      k != 0 ? 1u : acc_on);
+          }
+        }
+        umma_commit(&empty_bar[st]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // accumulator row: tap half (m / 64), input channel (m % 64)
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int rb = 0; rb < 5; ++rb) {
+      const int tap = 2 * rb + (m >> 6);
+      float* out = nullptr;
+      if (tap < 9)
+        out = p.part + (((size_t)split * 9 + tap) * p.Cin + (size_t)cc * 64 + (m & 63)) * p.Cout + (size_t)cb * 64;
+      else if (m == 64 && cc == 0 && p.bpart)
+        out = p.bpart + (size_t)split * p.Cout + (size_t)cb * 64;   // ones-row: sum over pixels of dy
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * 64);
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (out) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(out + c + g * 4) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+static bool wgrad_halo_ok(int H, int W, int Cin, int Cout, int stride) {
+  if (getenv("BVAE_CONV_NO_HALO")) return false;
+  return stride == 1 && H % 16 == 0 && W % 8 == 0 && Cin % 64 == 0 && Cout % 64 == 0;
+}
+
+static int conv_wgrad_halo(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
+                           int W, int Cin, int Cout, cudaStream_t st) {
+  WgHaloMaps maps;
+  WgHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.cin_chunks = Cin / 64;
+  p.co_blocks = Cout / 64;
+  p.tiles_w = W / 8;
+  p.tiles_h = H / 16;
+  p.m_tiles = pl.tiles_total;
+  p.tiles_per_split = pl.tiles_per_split;
+  p.Cin = Cin; p.Cout = Cout;
+  p.stages = 5;
+  p.ones_off = (uint32_t)p.stages * WH_STAGE;
+  p.bar_off = p.ones_off + 3072;
+  p.part = part;
+  p.bpart = bpart;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint32_t box[4] = {64u, 10u, 18u, 1u};
+    int rc = make_map(&maps.x, x, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    const uint32_t box[4] = {64u, 8u, 16u, 1u};
+    int rc = make_map(&maps.dy, dy, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + p.bar_off + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad_halo: cudaFuncSetAttribute");
+    configured = true;
+  }
+  dim3 grid(p.cin_chunks * p.co_blocks, pl.splits);
+  conv_wgrad_halo_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p);
+  BVAE_LAUNCH_CHECK("conv_wgrad_halo");
+  return BVAE_OK;
+}
+
 // Column sums of dy (bias gradient), fp32 partials [chunk][C]; memory bound, one pass over dy.
 __global__ void __launch_bounds__(256)
     colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ bpart, long long npix, int C, int cv,
@@ -191,6 +390,7 @@ __global__ void __launch_bounds__(256)
 }
 
 bool conv_tc_wgrad_supported(int H, int W, int Cin, int Cout, int stride) {
+  if (wgrad_halo_ok(H, W, Cin, Cout, stride)) return true;
   if (Cin % 64 || Cout % 64) return false;
   if (Cout > 256 && Cout % 256) return false;
   if (Cout < 256 && (Cout & (Cout - 1))) return false;  // 64, 128, 256
@@ -202,6 +402,20 @@ bool conv_tc_wgrad_supported(int H, int W, int Cin, int Cout, int stride) {
 
 WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int stride) {
   WgradTcPlan pl;
+  if (wgrad_halo_ok(H, W, Cin, Cout, stride)) {
+    pl.bn = 64; pl.slots = 5; pl.groups = (Cin / 64) * (Cout / 64);
+    pl.tiles_total = B * (H / 16) * (W / 8);
+    int splits = num_sms() / pl.groups;
+    if (splits < 1) splits = 1;
+    if (splits > pl.tiles_total) splits = pl.tiles_total;
+    pl.tiles_per_split = (pl.tiles_total + splits - 1) / splits;
+    pl.splits = (pl.tiles_total + pl.tiles_per_split - 1) / pl.tiles_per_split;
+    pl.bias_chunks = pl.splits;
+    pl.bias_pix_per_chunk = 0;
+    pl.part_bytes = align_up((size_t)pl.splits * 9 * Cin * Cout * sizeof(float), 256);
+    pl.bpart_bytes = align_up((size_t)pl.splits * Cout * sizeof(float), 256);
+    return pl;
+  }
   const int OW = (W - 1) / stride + 1, OH = (H - 1) / stride + 1;
   int tw, th, tn;
   tile_geom(OW, OH, &tw, &th, &tn, WG_PIX);
@@ -241,6 +455,7 @@ WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int strid
 
 int conv_tc_wgrad(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
                   int W, int Cin, int Cout, int stride, cudaStream_t st) {
+  if (wgrad_halo_ok(H, W, Cin, Cout, stride)) return conv_wgrad_halo(x, dy, part, bpart, pl, B, H, W, Cin, Cout, st);
   WgMaps maps;
   WgParams p;
   memset(&p, 0, sizeof(p));
