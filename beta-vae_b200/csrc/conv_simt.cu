@@ -338,26 +338,43 @@ __global__ void __launch_bounds__(256)
 }
 
 // dw[co][ci][t] = sum_split part[split][t][ci][co];  dbias[co] = sum_split bpart[split][co]
+// 64 consecutive elements x 4 split-groups per CTA: coalesced 256-byte rows, four loads in flight per
+// thread and a fixed-order combine in shared memory (deterministic).
 __global__ void __launch_bounds__(256)
     conv_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart, float* __restrict__ dw,
                              float* __restrict__ dbias, int Cin, int Cout, int splits, int bsplits) {
+  __shared__ float sm[4][64];
   const long long total = 9LL * Cin * Cout;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + Cout;
-       i += (long long)gridDim.x * blockDim.x) {
+  const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (long long base = (long long)blockIdx.x * 64; base < total + Cout; base += (long long)gridDim.x * 64) {
+    const long long i = base + e;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (i < total) {
-      // i indexes the partial layout [t][ci][co] so reads are coalesced
-      const int co = (int)(i % Cout);
-      const int ci = (int)((i / Cout) % Cin);
-      const int t = (int)(i / ((long long)Cout * Cin));
-      float acc = 0.f;
-      for (int s = 0; s < splits; ++s) acc += part[(size_t)s * total + i];
-      dw[((size_t)co * Cin + ci) * 9 + t] = acc;
-    } else if (dbias) {
+      int s = grp;
+      for (; s + 12 < splits; s += 16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += part[(size_t)(s + 4 * u) * total + i];
+      }
+      for (; s < splits; s += 4) acc[0] += part[(size_t)s * total + i];
+    } else if (i < total + Cout && dbias) {
       const int co = (int)(i - total);
-      float acc = 0.f;
-      for (int s = 0; s < bsplits; ++s) acc += bpart[(size_t)s * Cout + co];
-      dbias[co] = acc;
+      for (int s = grp; s < bsplits; s += 4) acc[0] += bpart[(size_t)s * Cout + co];
     }
+    sm[grp][e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (grp == 0) {
+      const float v = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
+      if (i < total) {
+        // i indexes the partial layout [t][ci][co]
+        const int co = (int)(i % Cout);
+        const int ci = (int)((i / Cout) % Cin);
+        const int t = (int)(i / ((long long)Cout * Cin));
+        dw[((size_t)co * Cin + ci) * 9 + t] = v;
+      } else if (i < total + Cout && dbias) {
+        dbias[(int)(i - total)] = v;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -367,8 +384,8 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 template <typename TX, typename TD>
 __global__ void __launch_bounds__(256)
-    conv_smallcin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __restrict__ part,
-                               float* __restrict__ bpart, int B, int H, int W, int Cin, int Ho, int Wo, int Cout,
+    conv_smallcin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, double* __restrict__ part,
+                               double* __restrict__ bpart, int B, int H, int W, int Cin, int Ho, int Wo, int Cout,
                                int stride, int cv, int rows, int pix_per_chunk) {
   constexpr int V = Vec16<TD>::N;
   extern __shared__ float sm[];  // [rows][Cout]
@@ -409,34 +426,49 @@ __global__ void __launch_bounds__(256)
       double a = 0.0;  // x > 0 and sum(dy) ~ 0 after GroupNorm: keep the cancellation exact-ish
       for (int r = 0; r < rows; ++r) a += (double)sm[r * Cout + c];
       if (t < 9)
-        part[(((size_t)chunk * Cin + ci) * 9 + t) * Cout + c] = (float)a;
+        part[(((size_t)chunk * Cin + ci) * 9 + t) * Cout + c] = a;   // double partials: the chunks cancel heavily
       else if (ci == 0 && bpart)
-        bpart[(size_t)chunk * Cout + c] = (float)a;
+        bpart[(size_t)chunk * Cout + c] = a;
     }
   }
 }
 
-// dw[co][ci][t] = sum_chunk part[chunk][ci][t][co]
+// dw[co][ci][t] = sum_chunk part[chunk][ci][t][co]; 64 elements x 4 chunk-groups per CTA, fixed-order combine
 __global__ void __launch_bounds__(256)
-    conv_smallcin_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart,
+    conv_smallcin_wgrad_reduce_kernel(const double* __restrict__ part, const double* __restrict__ bpart,
                                       float* __restrict__ dw, float* __restrict__ dbias, int Cin, int Cout,
                                       int chunks) {
+  __shared__ double sm[4][64];
   const long long total = 9LL * Cin * Cout;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + Cout;
-       i += (long long)gridDim.x * blockDim.x) {
+  const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (long long base = (long long)blockIdx.x * 64; base < total + Cout; base += (long long)gridDim.x * 64) {
+    const long long i = base + e;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     if (i < total) {
-      const int co = (int)(i % Cout);
-      const int t = (int)((i / Cout) % 9);
-      const int ci = (int)(i / (9LL * Cout));
-      double acc = 0.0;
-      for (int s = 0; s < chunks; ++s) acc += (double)part[(size_t)s * total + i];
-      dw[((size_t)co * Cin + ci) * 9 + t] = (float)acc;
-    } else if (dbias) {
+      int s = grp;
+      for (; s + 12 < chunks; s += 16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += part[(size_t)(s + 4 * u) * total + i];
+      }
+      for (; s < chunks; s += 4) acc[0] += part[(size_t)s * total + i];
+    } else if (i < total + Cout && dbias) {
       const int co = (int)(i - total);
-      float acc = 0.f;
-      for (int s = 0; s < chunks; ++s) acc += bpart[(size_t)s * Cout + co];
-      dbias[co] = acc;
+      for (int s = grp; s < chunks; s += 4) acc[0] += bpart[(size_t)s * Cout + co];
     }
+    sm[grp][e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (grp == 0) {
+      const double v = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
+      if (i < total) {
+        const int co = (int)(i % Cout);
+        const int t = (int)((i / Cout) % 9);
+        const int ci = (int)(i / (9LL * Cout));
+        dw[((size_t)co * Cin + ci) * 9 + t] = (float)v;
+      } else if (i < total + Cout && dbias) {
+        dbias[(int)(i - total)] = (float)v;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -462,8 +494,8 @@ static WgradPlan wgrad_plan(int B, int H, int W, int Cin, int Cout, int stride) 
     if (pc < 64) pc = 64;
     pl.pix_per_split = (int)pc;
     pl.splits = (int)((Mpix + pc - 1) / pc);
-    pl.bytes = align_up((size_t)pl.splits * Cin * 9 * Cout * sizeof(float), 256) +
-               align_up((size_t)pl.splits * Cout * sizeof(float), 256);
+    pl.bytes = align_up((size_t)pl.splits * Cin * 9 * Cout * sizeof(double), 256) +
+               align_up((size_t)pl.splits * Cout * sizeof(double), 256);
   } else {
     const long long tiles = (long long)cdiv(Cin, WM) * cdiv(Cout, WN) * 9;
     long long want = (4LL * 148 + tiles - 1) / tiles;  // ~4 waves worth of CTAs
@@ -489,17 +521,18 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, float* dbias, 
   if (pl.small) {
     constexpr int V = Vec16<TD>::N;
     BVAE_REQUIRE(Cout % V == 0 && Cout / V <= 256, BVAE_ERR_UNSUPPORTED, "conv3x3_wgrad(small Cin): Cout=%d", Cout);
-    float* bpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) +
-                                            align_up((size_t)pl.splits * Cin * 9 * Cout * sizeof(float), 256));
+    double* dpart = reinterpret_cast<double*>(ws);
+    double* bpart = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) +
+                                              align_up((size_t)pl.splits * Cin * 9 * Cout * sizeof(double), 256));
     const int cv = Cout / V, rows = 256 / cv > 0 ? 256 / cv : 1;
     dim3 grid(pl.splits, Cin);
     conv_smallcin_wgrad_kernel<TX, TD><<<grid, cv * rows, (size_t)rows * Cout * sizeof(float), st>>>(
-        (const TX*)x, (const TD*)dy, part, dbias ? bpart : nullptr, B, H, W, Cin, Ho, Wo, Cout, stride, cv, rows,
+        (const TX*)x, (const TD*)dy, dpart, dbias ? bpart : nullptr, B, H, W, Cin, Ho, Wo, Cout, stride, cv, rows,
         pl.pix_per_split);
     BVAE_LAUNCH_CHECK("conv_smallcin_wgrad");
     const long long total = 9LL * Cin * Cout + Cout;
-    conv_smallcin_wgrad_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout,
-                                                                                pl.splits);
+    conv_smallcin_wgrad_reduce_kernel<<<(int)((total + 63) / 64), 256, 0, st>>>(dpart, bpart, dw, dbias, Cin, Cout,
+                                                                              pl.splits);
     BVAE_LAUNCH_CHECK("conv_smallcin_wgrad_reduce");
     return BVAE_OK;
   }
@@ -511,7 +544,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, float* dbias, 
                                                   Cin, Ho, Wo, Cout, stride, pl.pix_per_split);
   BVAE_LAUNCH_CHECK("conv_wgrad");
   const long long total = 9LL * Cin * Cout + Cout;
-  long long blocks = (total + 255) / 256;
+  long long blocks = (total + 63) / 64;
   if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
   conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.splits);
   BVAE_LAUNCH_CHECK("conv_wgrad_reduce");
@@ -662,7 +695,7 @@ extern "C" int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, floa
     const int rc = conv_tc_wgrad(x, dy, part, dbias ? bpart : nullptr, pl, B, H, W, Cin, Cout, stride, st);
     if (rc != BVAE_OK) return rc;
     const long long total = 9LL * Cin * Cout + Cout;
-    long long blocks = (total + 255) / 256;
+    long long blocks = (total + 63) / 64;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
     conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks);
     BVAE_LAUNCH_CHECK("conv_wgrad_reduce");

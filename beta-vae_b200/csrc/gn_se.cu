@@ -167,15 +167,26 @@ __global__ void __launch_bounds__(256)
   float* hid = sm + C;
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, q = 0.f;
-    for (int k = 0; k < nchunks; ++k) {
-      const size_t o = ((size_t)b * nchunks + k) * C + c;
-      a += cpart[o];
-      q += xpart[o];
+    // four independent chains keep four loads per array in flight (the serial form is latency bound)
+    double a[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+    const float* cp = cpart + (size_t)b * nchunks * C + c;
+    const float* xp = xpart + (size_t)b * nchunks * C + c;
+    int k = 0;
+    for (; k + 4 <= nchunks; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] += (double)cp[(size_t)(k + u) * C];
+        q[u] += (double)xp[(size_t)(k + u) * C];
+      }
     }
-    cpos[(size_t)b * C + c] = a;
-    spos[(size_t)b * C + c] = q;
-    pool[c] = (gamma[c] * q + beta[c] * a) / (float)P;  // mean over pixels of relu(gn(y))
+    for (; k < nchunks; ++k) {
+      a[0] += (double)cp[(size_t)k * C];
+      q[0] += (double)xp[(size_t)k * C];
+    }
+    const float as = (float)((a[0] + a[1]) + (a[2] + a[3])), qs = (float)((q[0] + q[1]) + (q[2] + q[3]));
+    cpos[(size_t)b * C + c] = as;
+    spos[(size_t)b * C + c] = qs;
+    pool[c] = (gamma[c] * qs + beta[c] * as) / (float)P;  // mean over pixels of relu(gn(y))
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -192,7 +203,9 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {  // gate = sigmoid(W2 hidden + b2)
     float acc = b2[c];
-    for (int j = 0; j < R; ++j) acc = fmaf(w2[(size_t)c * R + j], hid[j], acc);
+    const float* wr = w2 + (size_t)c * R;
+#pragma unroll 8
+    for (int j = 0; j < R; ++j) acc = fmaf(wr[j], hid[j], acc);
     gate[(size_t)b * C + c] = 1.0f / (1.0f + expf(-acc));
   }
 }
@@ -316,13 +329,22 @@ __global__ void __launch_bounds__(256)
   const int b = blockIdx.x;
   const bool has_se = (w1 != nullptr);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double ad = 0.0, qd = 0.0;
-    for (int k = 0; k < nchunks; ++k) {
-      const size_t o = ((size_t)b * nchunks + k) * C + c;
-      ad += (double)a1part[o];
-      qd += (double)a2part[o];
+    double adv[4] = {0.0, 0.0, 0.0, 0.0}, qdv[4] = {0.0, 0.0, 0.0, 0.0};
+    const float* p1 = a1part + (size_t)b * nchunks * C + c;
+    const float* p2 = a2part + (size_t)b * nchunks * C + c;
+    int k = 0;
+    for (; k + 4 <= nchunks; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        adv[u] += (double)p1[(size_t)(k + u) * C];
+        qdv[u] += (double)p2[(size_t)(k + u) * C];
+      }
     }
-    const float a = (float)ad, q = (float)qd;
+    for (; k < nchunks; ++k) {
+      adv[0] += (double)p1[(size_t)k * C];
+      qdv[0] += (double)p2[(size_t)k * C];
+    }
+    const float a = (float)((adv[0] + adv[1]) + (adv[2] + adv[3])), q = (float)((qdv[0] + qdv[1]) + (qdv[2] + qdv[3]));
     A1[c] = a;
     A2[c] = q;
     if (has_se) {
@@ -353,6 +375,7 @@ __global__ void __launch_bounds__(256)
     float g1, g2;
     if (has_se) {
       float dp = 0.f;
+#pragma unroll 8
       for (int j = 0; j < R; ++j) dp = fmaf(dz1[j], w1[(size_t)j * C + c], dp);
       dp /= (float)P;
       dpoolo[(size_t)b * C + c] = dp;
@@ -384,43 +407,54 @@ __global__ void __launch_bounds__(256)
                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
                          float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
                          float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int has_se) {
-  // job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R]
+  // job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R].
+  // One WARP per job, lanes stride over the batch (the per-thread serial loop over B was latency bound).
   const long long n_gb = C, n_w2 = has_se ? (long long)C * R : 0, n_w1 = n_w2, n_b1 = has_se ? R : 0;
   const long long total = n_gb + n_w2 + n_w1 + n_b1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp0; i < total; i += nwarps) {
     if (i < n_gb) {
       const int c = (int)i;
       float dg = 0.f, db = 0.f, d2 = 0.f;
-      for (int b = 0; b < B; ++b) {
+      for (int b = lane; b < B; b += 32) {
         dg += G2[(size_t)b * C + c];
         db += G1[(size_t)b * C + c];
         if (has_se) d2 += dz2[(size_t)b * C + c];
       }
-      dgamma[c] = dg;
-      dbeta[c] = db;
-      if (has_se) db2[c] = d2;
+      dg = warp_sum(dg);
+      db = warp_sum(db);
+      d2 = warp_sum(d2);
+      if (lane == 0) {
+        dgamma[c] = dg;
+        dbeta[c] = db;
+        if (has_se) db2[c] = d2;
+      }
     } else if (i < n_gb + n_w2) {
       const long long k = i - n_gb;
       const int c = (int)(k / R), j = (int)(k % R);
       float acc = 0.f;
-      for (int b = 0; b < B; ++b) acc = fmaf(dz2[(size_t)b * C + c], hidden[(size_t)b * R + j], acc);
-      dw2[k] = acc;
+      for (int b = lane; b < B; b += 32) acc = fmaf(dz2[(size_t)b * C + c], hidden[(size_t)b * R + j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) dw2[k] = acc;
     } else if (i < n_gb + n_w2 + n_w1) {
       const long long k = i - n_gb - n_w2;
       const int j = (int)(k / C), c = (int)(k % C);
       float acc = 0.f;
       const float gc = gamma[c], bc = beta[c];
-      for (int b = 0; b < B; ++b) {
+      for (int b = lane; b < B; b += 32) {
         const float pool = (gc * spos[(size_t)b * C + c] + bc * cpos[(size_t)b * C + c]) / (float)P;
         acc = fmaf(dz1[(size_t)b * R + j], pool, acc);
       }
-      dw1[k] = acc;
+      acc = warp_sum(acc);
+      if (lane == 0) dw1[k] = acc;
     } else {
       const int j = (int)(i - n_gb - n_w2 - n_w1);
       float acc = 0.f;
-      for (int b = 0; b < B; ++b) acc += dz1[(size_t)b * R + j];
-      db1[j] = acc;
+      for (int b = lane; b < B; b += 32) acc += dz1[(size_t)b * R + j];
+      acc = warp_sum(acc);
+      if (lane == 0) db1[j] = acc;
     }
   }
 }
@@ -549,8 +583,8 @@ static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, con
       P, C, R);
   BVAE_LAUNCH_CHECK("gn_bwd_mid");
   const long long jobs = (long long)C + (has_se ? 2LL * C * R + R : 0);
-  int pblocks = (int)((jobs + 255) / 256);
-  if (pblocks > 4 * num_sms()) pblocks = 4 * num_sms();
+  int pblocks = (int)((jobs + 7) / 8);  // one warp per job, 8 warps per CTA
+  if (pblocks > 8 * num_sms()) pblocks = 8 * num_sms();
   gn_bwd_params_kernel<<<pblocks, 256, 0, st>>>(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma,
                                                 dbeta, dw1, db1, dw2, db2, B, P, C, R, has_se ? 1 : 0);
   BVAE_LAUNCH_CHECK("gn_bwd_params");
