@@ -350,7 +350,14 @@ def cuda_main(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by a captured CUDA graph can stall destroy_process_group();
+        # everything is flushed, so leave through a barrier and a hard exit
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -46,6 +46,10 @@ bool conv_halo_supported(int H, int W, int K, int N);
 int conv_halo_launch(const void* src, const void* wp_nk, const float* bias, void* dst, int B, int H, int W, int K, int N,
                      int dgrad, cudaStream_t st);
 
+bool conv_halo_final_supported(int H, int W, int C, int Co);
+int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, const float* target, float* recon,
+                        double* lpart, int* n_lpart, int loss_type, int B, int H, int W, int C, int Co, cudaStream_t st);
+
 // ---- wgrad (conv_tc_wgrad.cu) ----
 struct WgradTcPlan {
   int bn, slots, groups;           // co tile, accumulator slots per CTA, row-block groups

@@ -52,6 +52,11 @@ struct HaloParams {
   uint32_t a_off, b_off, bar_off;
   __nv_bfloat16* dst;
   const float* bias;
+  // EPI == 1 (final_conv + sigmoid + reconstruction loss, src/models/beta_vae.py:163-164,185-192)
+  const float* target;     // [B][Co][H][W] fp32 or null
+  float* recon;            // [B][Co][H][W] fp32
+  double* lpart;           // [gridDim.x * 4] per-warp partial sums of the elementwise loss, or null
+  int loss_type, Co;
 };
 
 struct HaloMaps {
@@ -73,10 +78,20 @@ __device__ __forceinline__ uint64_t kmajor_desc_sbo(uint32_t saddr, uint32_t sbo
   return d;
 }
 
+__device__ __forceinline__ float final_elem_loss(float r, float x, int type) {
+  if (type == BVAE_LOSS_MSE) {
+    const float d = r - x;
+    return d * d;
+  }
+  if (type == BVAE_LOSS_L1) return fabsf(r - x);
+  const float lp = fmaxf(logf(r), -100.f), l1p = fmaxf(logf(1.f - r), -100.f);  // F.binary_cross_entropy clamps at -100
+  return -(x * lp + (1.f - x) * l1p);
+}
+
 // Window j = (r, s) of the halo starts ((r * 10) + s) pixel rows into the buffer.  fprop uses weight tap j with
 // window j; dgrad (flipped kernel) uses weight tap 8 - j with window j -- the producer stores tap `wtap(j)` in
 // weight slot j, so the MMA loop is identical for both and fully unrolled with constant offsets.
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int EPI>
 __global__ void __launch_bounds__(HL_THREADS, 1)
     conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
     mbar_init(b_res, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.N; i += HL_THREADS) bias_sm[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.N; i += HL_THREADS) bias_sm[i] = (p.bias && (EPI == 0 || i < p.Co)) ? p.bias[i] : 0.f;
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
     const int r = q * 32 + lane;            // pixel inside the 16x8 tile
     const int hl = r / HL_TW, wl = r % HL_TW;
     uint32_t iu = 0;
+    float lsum = 0.f;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const int nt = u % p.n_tiles, mg = u / p.n_tiles;
       const int n0 = nt * BN;
@@ -239,33 +255,55 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
         mt /= p.tiles_w;
         const int h0 = (mt % p.tiles_h) * HL_TH;
         const int b = mt / p.tiles_h;
-        __nv_bfloat16* out = p.dst + (((size_t)b * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl)) * p.N + n0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.tm * BN) + (uint32_t)(m * BN);
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)c, v);
+        if constexpr (EPI == 1) {
+          // columns 0..Co-1 hold the logits; sigmoid, write recon (NCHW fp32), accumulate the loss
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
           tmem_ld_wait();
-          const float4* bq = reinterpret_cast<const float4*>(bias_sm + n0 + c);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 b0 = bq[2 * g], b1 = bq[2 * g + 1];
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint32_t pk[4];
+          for (int co = 0; co < 3; ++co) {
+            if (co >= p.Co) break;
+            const float logit = __uint_as_float(v[co]) + bias_sm[co];
+            const float rr = 1.f / (1.f + expf(-logit));
+            const size_t o = (((size_t)b * p.Co + co) * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl);
+            p.recon[o] = rr;
+            if (p.target) lsum += final_elem_loss(rr, p.target[o], p.loss_type);
+          }
+        } else {
+          __nv_bfloat16* out = p.dst + (((size_t)b * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl)) * p.N + n0;
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (uint32_t)c, v);
+            tmem_ld_wait();
+            const float4* bq = reinterpret_cast<const float4*>(bias_sm + n0 + c);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float f0 = __uint_as_float(v[g * 8 + 2 * e]) + bb[2 * e];
-              const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + bb[2 * e + 1];
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int g = 0; g < 4; ++g) {
+              const float4 b0 = bq[2 * g], b1 = bq[2 * g + 1];
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float f0 = __uint_as_float(v[g * 8 + 2 * e]) + bb[2 * e];
+                const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + bb[2 * e + 1];
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if constexpr (EPI == 1) {
+      if (p.lpart) {
+        const double s = warp_sum((double)lsum);
+        if (lane == 0) p.lpart[blockIdx.x * 4 + q] = s;
+      }
     }
   }
   tc_fence_before();
@@ -364,12 +402,72 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
     if (grid < p.n_tiles) grid = p.n_tiles;
   }
   void (*kern)(const HaloMaps, const HaloParams) = nullptr;
-  if (p.resident) kern = p.bn == 64 ? conv_halo_tc_kernel<64, true> : (p.bn == 128 ? conv_halo_tc_kernel<128, true> : conv_halo_tc_kernel<256, true>);
-  else            kern = p.bn == 64 ? conv_halo_tc_kernel<64, false> : (p.bn == 128 ? conv_halo_tc_kernel<128, false> : conv_halo_tc_kernel<256, false>);
+  if (p.resident) kern = p.bn == 64 ? conv_halo_tc_kernel<64, true, 0> : (p.bn == 128 ? conv_halo_tc_kernel<128, true, 0> : conv_halo_tc_kernel<256, true, 0>);
+  else            kern = p.bn == 64 ? conv_halo_tc_kernel<64, false, 0> : (p.bn == 128 ? conv_halo_tc_kernel<128, false, 0> : conv_halo_tc_kernel<256, false, 0>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX);
   if (e != cudaSuccess) return cuda_fail(e, "conv_halo: cudaFuncSetAttribute");
   kern<<<grid, HL_THREADS, smem, st>>>(maps, p);
   BVAE_LAUNCH_CHECK("conv_halo_tc");
+  return BVAE_OK;
+}
+
+// final_conv (C -> Co <= 3) + sigmoid + reconstruction loss on the same halo pipeline: the output-channel
+// dimension is padded to the smallest UMMA N (16) -- `wp16` is the [9][16][C] bf16 pack with zero rows
+// beyond Co -- and the epilogue reads the Co logit columns straight from TMEM.
+bool conv_halo_final_supported(int H, int W, int C, int Co) {
+  if (getenv("BVAE_CONV_NO_HALO")) return false;
+  return H % HL_TH == 0 && W % HL_TW == 0 && C % 64 == 0 && C <= 256 && Co >= 1 && Co <= 3;
+}
+
+int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, const float* target, float* recon,
+                        double* lpart, int* n_lpart, int loss_type, int B, int H, int W, int C, int Co,
+                        cudaStream_t st) {
+  HaloMaps maps;
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.kchunks = C / 64;
+  p.tiles_w = W / HL_TW;
+  p.tiles_h = H / HL_TH;
+  p.m_tiles = p.tiles_w * p.tiles_h * B;
+  p.B = B; p.H = H; p.W = W; p.N = 16;
+  p.bias = bias;
+  p.target = target; p.recon = recon; p.lpart = lpart; p.loss_type = loss_type; p.Co = Co;
+  p.resident = 1; p.bn = 16; p.tm = 1; p.sb = 0; p.n_tiles = 1;
+  const size_t bar_bytes = 256 + 16 * sizeof(float) + 64;
+  const size_t wbytes = (size_t)9 * C * 16 * 2;
+  int sa = (int)((HL_SMEM_MAX - 1024 - bar_bytes - wbytes) / HL_HALO_SLOT);
+  p.sa = sa > 8 ? 8 : sa;
+  if (const char* e = getenv("BVAE_HALO_SA")) p.sa = atoi(e);  // dev knob
+  p.b_off = 0;
+  p.a_off = (uint32_t)align_up(wbytes, 1024);
+  p.bar_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;
+  const size_t smem = 1024 + p.bar_off + bar_bytes;
+  p.m_groups = p.m_tiles;
+  p.units = p.m_tiles;
+  p.nbuf = 2;
+  p.tmem_cols = 32;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    const uint32_t box[4] = {64u, (uint32_t)HL_HW, (uint32_t)HL_HH, 1u};
+    int rc = make_map(&maps.x, h, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)C, 16, 9};
+    const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)C * 16 * 2};
+    const uint32_t box[3] = {64u, 16u, 1u};
+    int rc = make_map(&maps.w, wp16, 3, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  const int sms = num_sms();
+  const int grid = p.units < sms ? p.units : sms;
+  auto kern = conv_halo_tc_kernel<16, true, 1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_halo_final: cudaFuncSetAttribute");
+  kern<<<grid, HL_THREADS, smem, st>>>(maps, p);
+  BVAE_LAUNCH_CHECK("conv_halo_final_fwd");
+  *n_lpart = grid * 4;
   return BVAE_OK;
 }
 

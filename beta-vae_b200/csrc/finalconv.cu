@@ -12,7 +12,10 @@
 //   dw[c][t]   += h[q][c] * dlogit[q - off_t]
 // so h is read exactly once and dh written exactly once.  dw/db leave each CTA as fp32
 // partials that a second kernel sums in fixed order (deterministic).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace bvae {
 
@@ -233,6 +236,7 @@ struct FinalWs {
   float* dlogit;  // [B][Co][H][W]
   float* wpart;   // [kFcMaxCtas][Co][9][C]
   float* bpart;   // [kFcMaxCtas][Co]
+  __nv_bfloat16* wp16;  // [9][16][C] bf16 weights for the tcgen05 forward (rows >= Co are zero)
   size_t bytes;
 };
 static FinalWs final_ws_carve(void* base, int B, int H, int W, int C, int Co) {
@@ -248,8 +252,24 @@ static FinalWs final_ws_carve(void* base, int B, int H, int W, int C, int Co) {
   w.dlogit = reinterpret_cast<float*>(take((size_t)B * Co * H * W * sizeof(float)));
   w.wpart = reinterpret_cast<float*>(take((size_t)kFcMaxCtas * Co * 9 * C * sizeof(float)));
   w.bpart = reinterpret_cast<float*>(take((size_t)kFcMaxCtas * Co * sizeof(float)));
+  w.wp16 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * 16 * C * sizeof(__nv_bfloat16)));
   w.bytes = off;
   return w;
+}
+
+// w [Co][C][3][3] fp32 -> wp16 [9][16][C] bf16, zero rows for co >= Co
+__global__ void __launch_bounds__(256) final_pack16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                           int C, int Co) {
+  const int total = 9 * 16 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, co = (i / C) % 16, t = i / (16 * C);
+    wp[i] = __float2bfloat16_rn(co < Co ? w[((size_t)co * C + c) * 9 + t] : 0.f);
+  }
+}
+
+static bool final_tc_env_off() {
+  const char* env = getenv("BVAE_CONV_SIMT");
+  return env != nullptr && env[0] == '1';
 }
 
 template <typename T>
@@ -263,6 +283,20 @@ static int final_fwd_impl(const void* h, const float* w, const float* b, const f
   const size_t sm = (size_t)Co * 9 * C * sizeof(float);
   BVAE_REQUIRE(sm <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "finalconv: C=%d too large", C);
   const bool want_loss = target != nullptr && loss_out != nullptr;
+  if (sizeof(T) == 2 && !final_tc_env_off() && conv_halo_final_supported(H, W, C, Co)) {
+    // tcgen05 path: the 3x3xC contraction runs on the tensor cores (N padded to 16), fused epilogue
+    final_pack16_kernel<<<cdiv(9 * 16 * C, 256), 256, 0, st>>>(w, fw.wp16, C, Co);
+    BVAE_LAUNCH_CHECK("final_pack16");
+    int n_lpart = 0;
+    const int rc = conv_halo_final_fwd(h, fw.wp16, b, want_loss ? target : nullptr, recon, want_loss ? fw.lpart : nullptr,
+                                       &n_lpart, loss_type, B, H, W, C, Co, st);
+    if (rc != BVAE_OK) return rc;
+    if (want_loss) {
+      loss_final_kernel<<<1, 256, 0, st>>>(fw.lpart, n_lpart, 1.0 / (double)B, loss_out);
+      BVAE_LAUNCH_CHECK("loss_final");
+    }
+    return BVAE_OK;
+  }
   finalconv_fwd_kernel<T><<<g.ctas, g.threads, sm, st>>>((const T*)h, w, b, want_loss ? target : nullptr, recon,
                                                          want_loss ? fw.lpart : nullptr, loss_type, B, H, W, C, Co,
                                                          g.cv);

@@ -311,7 +311,8 @@ def test_fc_dec(B, L, Cc, hw, zc, prec):
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("loss", ["mse", "l1", "bce"])
-@pytest.mark.parametrize("B,H,W,Cc,Co", [(2, 8, 8, 8, 1), (3, 5, 7, 16, 1), (2, 16, 16, 64, 1), (2, 8, 8, 8, 3)])
+@pytest.mark.parametrize("B,H,W,Cc,Co", [(2, 8, 8, 8, 1), (3, 5, 7, 16, 1), (2, 16, 16, 64, 1), (2, 8, 8, 8, 3),
+                                         (3, 32, 16, 64, 3), (5, 128, 128, 64, 1)])
 def test_finalconv_sigmoid_recon(B, H, W, Cc, Co, loss, prec):
     ops = _ops()
     from bvae_rt.lib import LOSS
@@ -334,13 +335,19 @@ def test_finalconv_sigmoid_recon(B, H, W, Cc, Co, loss, prec):
     hd = nhwc(h.detach(), dtype).requires_grad_(True)
     wd, bd = D(w).requires_grad_(True), D(b).requires_grad_(True)
     rd, ld = ops.FinalConvSigmoidRecon.apply(hd, wd, bd, D(x), LOSS[loss])
-    assert rel_err(rd, r) <= 1e-5 and rel_err(ld, l) <= 1e-5     # fp32 math on (rounded) inputs in both modes
+    # fp32: exact fp32 math.  bf16: shapes the tcgen05 forward takes (H%16 == 0, W%8 == 0, C%64 == 0) use
+    # bf16-rounded weights, as the reference's conv2d does under autocast -> bf16 tolerance; the CUDA-core
+    # forward keeps fp32 weights
+    ftol = 1e-5 if (prec == "fp32" or H % 16 or W % 8 or Cc % 64) else 2e-3
+    assert rel_err(rd, r) <= ftol and rel_err(ld, l) <= ftol
     (ld * 1.3 + (rd * D(gr)).sum()).backward()
-    assert rel_err(nchw(hd.grad), h.grad) <= tol
-    assert rel_err(wd.grad, w.grad) <= 2e-5 and rel_err(bd.grad, b.grad) <= 2e-5
+    # l1: d|r-x| = sign(r-x) flips wherever the bf16-rounded weights move r across x (reference under autocast: same)
+    assert rel_err(nchw(hd.grad), h.grad) <= (3 * tol if (loss == "l1" and ftol != 1e-5) else tol)
+    gtol = 2e-5 if ftol == 1e-5 else (3 * tol if loss == "l1" else tol)   # db = sum of signed dlogit: bf16-rounded weights move it by ~1e-3..1e-2
+    assert rel_err(wd.grad, w.grad) <= gtol and rel_err(bd.grad, b.grad) <= gtol
     # decode-only form (no target)
     r2, _ = ops.FinalConvSigmoidRecon.apply(hd.detach(), wd.detach(), bd.detach(), None, 0)
-    assert rel_err(r2, r) <= 1e-5
+    assert rel_err(r2, r) <= ftol
 
 
 def test_adam_clip_step_matches_torch():
