@@ -337,6 +337,31 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// few splits: one thread per element
+__global__ void __launch_bounds__(256)
+    conv_wgrad_reduce_simple_kernel(const float* __restrict__ part, const float* __restrict__ bpart,
+                                    float* __restrict__ dw, float* __restrict__ dbias, int Cin, int Cout, int splits,
+                                    int bsplits) {
+  const long long total = 9LL * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + Cout;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < total) {
+      const int co = (int)(i % Cout);
+      const int ci = (int)((i / Cout) % Cin);
+      const int t = (int)(i / ((long long)Cout * Cin));
+      float acc = 0.f;
+#pragma unroll 4
+      for (int s = 0; s < splits; ++s) acc += part[(size_t)s * total + i];
+      dw[((size_t)co * Cin + ci) * 9 + t] = acc;
+    } else if (dbias) {
+      const int co = (int)(i - total);
+      float acc = 0.f;
+      for (int s = 0; s < bsplits; ++s) acc += bpart[(size_t)s * Cout + co];
+      dbias[co] = acc;
+    }
+  }
+}
+
 // dw[co][ci][t] = sum_split part[split][t][ci][co];  dbias[co] = sum_split bpart[split][co]
 // 64 consecutive elements x 4 split-groups per CTA: coalesced 256-byte rows, four loads in flight per
 // thread and a fixed-order combine in shared memory (deterministic).
@@ -376,6 +401,22 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
+}
+
+static int launch_wgrad_reduce(const float* part, const float* bpart, float* dw, float* dbias, int Cin, int Cout,
+                               int splits, int bsplits, cudaStream_t st) {
+  const long long total = 9LL * Cin * Cout + Cout;
+  if (splits >= 8) {
+    long long blocks = (total + 63) / 64;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, splits, bsplits);
+  } else {
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    conv_wgrad_reduce_simple_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, splits, bsplits);
+  }
+  BVAE_LAUNCH_CHECK("conv_wgrad_reduce");
+  return BVAE_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -543,12 +584,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, float* dbias, 
   conv_wgrad_kernel<TX, TD><<<grid, 256, 0, st>>>((const TX*)x, (const TD*)dy, part, dbias ? bpart : nullptr, B, H, W,
                                                   Cin, Ho, Wo, Cout, stride, pl.pix_per_split);
   BVAE_LAUNCH_CHECK("conv_wgrad");
-  const long long total = 9LL * Cin * Cout + Cout;
-  long long blocks = (total + 63) / 64;
-  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-  conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.splits);
-  BVAE_LAUNCH_CHECK("conv_wgrad_reduce");
-  return BVAE_OK;
+  return launch_wgrad_reduce(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.splits, st);
 }
 
 }  // namespace bvae
@@ -694,12 +730,7 @@ extern "C" int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, floa
     float* bpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
     const int rc = conv_tc_wgrad(x, dy, part, dbias ? bpart : nullptr, pl, B, H, W, Cin, Cout, stride, st);
     if (rc != BVAE_OK) return rc;
-    const long long total = 9LL * Cin * Cout + Cout;
-    long long blocks = (total + 63) / 64;
-    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks);
-    BVAE_LAUNCH_CHECK("conv_wgrad_reduce");
-    return BVAE_OK;
+    return launch_wgrad_reduce(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks, st);
   }
   if (x_dtype == BVAE_F32 && dy_dtype == BVAE_F32)
     return wgrad_launch<float, float>(x, dy, dw, dbias, ws, B, H, W, Cin, Cout, stride, st);

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int tn_i = tile / p.tiles_h;
   const int w0 = tw_i * p.tw, h0 = th_i * p.th, b0 = tn_i * p.tn;
   const int n0 = blockIdx.y * p.bn;
-  const int iters = p.ntaps * p.kchunks;
+  const int cls = blockIdx.z;                      // stride-2 dgrad: output parity class (po, pw) = (cls / 2, cls % 2)
+  const int iters = p.ntaps[cls] * p.kchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -75,17 +76,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===== TMA producer =====
     if (lane == 0) {
       tma_prefetch_desc(&maps.w);
+      int s = 0, t = 0, kc = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int t = it / p.kchunks, kc = it % p.kchunks;
-        const TcTap tap = p.taps[t];
+        const TcTap tap = p.taps[cls][t];
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + a_bytes;
         mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
         tma_load_4d(&maps.src[tap.map], &full_bar[s], a_dst, kc * p.kc, w0 + tap.dj, h0 + tap.di, b0);
         tma_load_3d(&maps.w, &full_bar[s], b_dst, kc * p.kc, n0, tap.widx);
+        if (++kc == p.kchunks) { kc = 0; ++t; }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -94,20 +96,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t row_bytes = p.kc * 2;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t desc_hi = kmajor_desc(0, row_bytes);     // everything but the address field
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        const uint64_t adesc = kmajor_desc(a_addr, row_bytes), bdesc = kmajor_desc(b_addr, row_bytes);
-        const int ksteps = p.kc / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+        const uint32_t a_addr = smem0 + (uint32_t)s * stage_bytes;
+        const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)((a_addr + a_bytes) >> 4);
+        // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units
+        umma_bf16(tmem_base, adesc, bdesc, idesc, it != 0 ? 1u : 0u);
+        if (p.kc >= 32) umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+        if (p.kc >= 64) {
+          umma_bf16(tmem_base, adesc + 4, bdesc + 4, idesc, 1u);
+          umma_bf16(tmem_base, adesc + 6, bdesc + 6, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       umma_commit(accum_bar);        // accumulator complete
     }
@@ -118,7 +124,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int wl = r % p.tw, hl = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
     const int b = b0 + nl, oi = h0 + hl, oj = w0 + wl;
     const bool valid = b < p.B;
-    __nv_bfloat16* out = p.dst + (((size_t)b * p.DH + (size_t)(oi * p.ds + p.po)) * p.DW + (size_t)(oj * p.ds + p.pw)) * p.N + n0;
+    const int po = p.ncls == 4 ? (cls >> 1) : 0, pw = p.ncls == 4 ? (cls & 1) : 0;
+    __nv_bfloat16* out = p.dst + (((size_t)b * p.DH + (size_t)(oi * p.ds + po)) * p.DW + (size_t)(oj * p.ds + pw)) * p.N + n0;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -200,7 +207,7 @@ static int launch_tc(const TcMaps& maps, TcParams& p, int m_tiles, cudaStream_t 
     if (e != cudaSuccess) return cuda_fail(e, "conv_tc: cudaFuncSetAttribute");
     configured = smem;
   }
-  dim3 grid(m_tiles, p.N / p.bn);
+  dim3 grid(m_tiles, p.N / p.bn, p.ncls);
   conv_tap_gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps, p);
   BVAE_LAUNCH_CHECK("conv_tap_gemm_tc");
   return BVAE_OK;
@@ -228,10 +235,12 @@ int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int
   p.tiles_w = OW / p.tw;
   p.tiles_h = OH / p.th;
   const int tiles_n = cdiv(B, p.tn);
+  for (long ctas = (long)p.tiles_w * p.tiles_h * tiles_n * (Cout / p.bn); ctas < 100 && p.bn > 64; ctas *= 2) p.bn >>= 1;
   p.B = B; p.N = Cout; p.DH = OH; p.DW = OW; p.ds = 1; p.po = 0; p.pw = 0;
   p.dst = reinterpret_cast<__nv_bfloat16*>(y);
   p.bias = bias;
-  p.ntaps = 9;
+  p.ncls = 1;
+  p.ntaps[0] = 9;
   const uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
   int rc;
   if (stride == 1) {
@@ -239,7 +248,7 @@ int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     rc = make_map(&maps.src[0], x, 4, dims, strides, box, p.kc * 2);
     if (rc) return rc;
-    for (int t = 0; t < 9; ++t) p.taps[t] = TcTap{0, (int8_t)(t / 3 - 1), (int8_t)(t % 3 - 1), (int8_t)t};
+    for (int t = 0; t < 9; ++t) p.taps[0][t] = TcTap{0, (int8_t)(t / 3 - 1), (int8_t)(t % 3 - 1), (int8_t)t};
   } else {
     // parity views: x[b, 2i+ph, 2j+pw, c]
     for (int ph = 0; ph < 2; ++ph)
@@ -255,7 +264,7 @@ int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int
       // input row 2*oh + r - 1: r=0 -> odd row, index oh-1; r=1 -> even row, index oh; r=2 -> odd row, index oh
       const int ph = (r == 1) ? 0 : 1, di = (r == 0) ? -1 : 0;
       const int pw = (s == 1) ? 0 : 1, dj = (s == 0) ? -1 : 0;
-      p.taps[t] = TcTap{(int8_t)(ph * 2 + pw), (int8_t)di, (int8_t)dj, (int8_t)t};
+      p.taps[0][t] = TcTap{(int8_t)(ph * 2 + pw), (int8_t)di, (int8_t)dj, (int8_t)t};
     }
   }
   rc = make_weight_map(&maps.w, wp, Cin, Cout, p.kc, p.bn);
@@ -278,6 +287,9 @@ int conv_tc_dgrad(const void* dy, const void* wpt, void* dx, int B, int H, int W
   p.tiles_w = GW / p.tw;
   p.tiles_h = GH / p.th;
   const int tiles_n = cdiv(B, p.tn);
+  for (long ctas = (long)p.tiles_w * p.tiles_h * tiles_n * (Cin / p.bn) * (stride == 2 ? 4 : 1); ctas < 100 && p.bn > 64;
+       ctas *= 2)
+    p.bn >>= 1;
   p.B = B; p.N = Cin; p.DH = H; p.DW = W;
   p.dst = reinterpret_cast<__nv_bfloat16*>(dx);
   p.bias = nullptr;
@@ -290,25 +302,28 @@ int conv_tc_dgrad(const void* dy, const void* wpt, void* dx, int B, int H, int W
   if (rc) return rc;
   if (stride == 1) {
     p.ds = 1; p.po = 0; p.pw = 0;
-    p.ntaps = 9;
-    for (int t = 0; t < 9; ++t) p.taps[t] = TcTap{0, (int8_t)(1 - t / 3), (int8_t)(1 - t % 3), (int8_t)t};
+    p.ncls = 1;
+    p.ntaps[0] = 9;
+    for (int t = 0; t < 9; ++t) p.taps[0][t] = TcTap{0, (int8_t)(1 - t / 3), (int8_t)(1 - t % 3), (int8_t)t};
     return launch_tc(maps, p, p.tiles_w * p.tiles_h * tiles_n, st);
   }
+  // stride 2: the four output parity classes are dense sub-convolutions; one launch, class = blockIdx.z
+  p.ds = 2; p.po = 0; p.pw = 0;
+  p.ncls = 4;
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw) {
-      p.ds = 2; p.po = ph; p.pw = pw;
-      p.ntaps = 0;
+      const int cls = ph * 2 + pw;
+      int n = 0;
       for (int r = 0; r < 3; ++r) {
         if ((ph + 1 - r) % 2 != 0) continue;
         for (int s = 0; s < 3; ++s) {
           if ((pw + 1 - s) % 2 != 0) continue;
-          p.taps[p.ntaps++] = TcTap{0, (int8_t)((ph + 1 - r) / 2), (int8_t)((pw + 1 - s) / 2), (int8_t)(r * 3 + s)};
+          p.taps[cls][n++] = TcTap{0, (int8_t)((ph + 1 - r) / 2), (int8_t)((pw + 1 - s) / 2), (int8_t)(r * 3 + s)};
         }
       }
-      rc = launch_tc(maps, p, p.tiles_w * p.tiles_h * tiles_n, st);
-      if (rc) return rc;
+      p.ntaps[cls] = n;
     }
-  return BVAE_OK;
+  return launch_tc(maps, p, p.tiles_w * p.tiles_h * tiles_n, st);
 }
 
 }  // namespace bvae

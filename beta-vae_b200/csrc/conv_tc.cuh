@@ -21,8 +21,9 @@ struct TcMaps {
 };
 
 struct TcParams {
-  int ntaps;
-  TcTap taps[9];
+  int ncls;                      // 1, or 4 output parity classes of a stride-2 dgrad (blockIdx.z)
+  int ntaps[4];
+  TcTap taps[4][9];
   int kc, kchunks;               // channels per chunk (64/32/16) and chunks per tap
   int bn;                        // output channels per CTA (UMMA N)
   int tw, th, tn;                // tile box: tw*th*tn = 128 pixels
