@@ -102,6 +102,13 @@ class PackCache:
     def bump(self):
         self._epoch += 1
 
+    def valid(self, key, params, dt):
+        ent = self._d.get((key, dt))
+        return ent is not None and ent[0] == (self._epoch,) + tuple((p._version, p.data_ptr()) for p in params)
+
+    def put(self, key, params, dt, val):
+        self._d[(key, dt)] = ((self._epoch,) + tuple((p._version, p.data_ptr()) for p in params), val)
+
     def get(self, key, params, dt, build):
         sig = (self._epoch,) + tuple((p._version, p.data_ptr()) for p in params)
         ent = self._d.get((key, dt))
@@ -125,6 +132,28 @@ def pack_conv(w, dt, transpose, layout=0):
     wp = torch.empty(shape, dtype=torch_dtype(dt), device=w.device)
     call("bvae_pack_conv_weight", _p(w), _p(wp), cout, cin, layout, 1 if transpose else 0, dt, _stream())
     return wp
+
+
+def pack_conv_many(jobs, dt):
+    """jobs: list of (weight [Cout,Cin,3,3] fp32, transpose, layout).  One launch; returns the packs in order."""
+    import ctypes as C
+    n = len(jobs)
+    outs = []
+    for w, transpose, layout in jobs:
+        cout, cin = w.shape[0], w.shape[1]
+        k, nn = (cout, cin) if transpose else (cin, cout)
+        outs.append(torch.empty((9, k, nn) if layout == 0 else (9, nn, k), dtype=torch_dtype(dt), device=w.device))
+    for lo in range(0, n, 32):
+        part = list(range(lo, min(n, lo + 32)))
+        m = len(part)
+        wa = (C.c_void_p * m)(*[_p(jobs[i][0]) for i in part])
+        oa = (C.c_void_p * m)(*[_p(outs[i]) for i in part])
+        co = (C.c_int * m)(*[jobs[i][0].shape[0] for i in part])
+        ci = (C.c_int * m)(*[jobs[i][0].shape[1] for i in part])
+        la = (C.c_int * m)(*[int(jobs[i][2]) for i in part])
+        tr = (C.c_int * m)(*[1 if jobs[i][1] else 0 for i in part])
+        call("bvae_pack_conv_weights", m, wa, oa, co, ci, la, tr, dt, _stream())
+    return outs
 
 
 def pack_heads(w_mu, w_lv, dt, C, P):

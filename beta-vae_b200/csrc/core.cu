@@ -61,6 +61,37 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, T* __restrict__ wp
   }
 }
 
+// Every conv weight of the model in ONE launch (blockIdx.y = job): the packs are re-made each step from the fp32
+// masters, and 16 separate 5-us launches cost more than the work.
+struct PackJob {
+  const float* w;
+  void* wp;
+  int Cout, Cin, layout, transpose;
+};
+struct PackJobs {
+  PackJob j[32];
+};
+template <typename T>
+__global__ void pack_conv_batched_kernel(const PackJobs jobs) {
+  const PackJob jb = jobs.j[blockIdx.y];
+  const int K = jb.transpose ? jb.Cout : jb.Cin, N = jb.transpose ? jb.Cin : jb.Cout;
+  const int KN = K * N, total = 9 * KN;
+  T* wp = reinterpret_cast<T*>(jb.wp);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i / KN, rem = i - t * KN;
+    int k, n;
+    if (jb.layout == 0) {
+      k = rem / N;
+      n = rem - k * N;
+    } else {
+      n = rem / K;
+      k = rem - n * K;
+    }
+    const int ci = jb.transpose ? n : k, co = jb.transpose ? k : n;
+    wp[i] = Elem<T>::from_f(jb.w[((size_t)co * jb.Cin + ci) * 9 + t]);
+  }
+}
+
 // wh[r][p*C + c] = (r < L ? w_mu : w_lv)[r % L][c*P + p]
 template <typename T>
 __global__ void pack_heads_kernel(const float* __restrict__ wmu, const float* __restrict__ wlv, T* __restrict__ wh,
@@ -209,6 +240,31 @@ extern "C" int bvae_pack_conv_weight(const float* w, void* wp, int Cout, int Cin
   else
     BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_conv_weight: dtype %d", dtype);
   BVAE_LAUNCH_CHECK("pack_conv_weight");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_pack_conv_weights(int n, const void* const* w, void* const* wp, const int* Cout, const int* Cin,
+                                      const int* layout, const int* transpose, int dtype, bvae_stream_t stream) {
+  BVAE_REQUIRE(n > 0 && n <= 32 && w && wp && Cout && Cin && layout && transpose, BVAE_ERR_ARG,
+               "pack_conv_weights: bad argument (1..32 jobs)");
+  PackJobs jobs;
+  long long big = 0;
+  for (int i = 0; i < n; ++i) {
+    BVAE_REQUIRE(w[i] && wp[i] && Cout[i] > 0 && Cin[i] > 0, BVAE_ERR_ARG, "pack_conv_weights: job %d", i);
+    BVAE_REQUIRE(9LL * Cout[i] * Cin[i] < (1LL << 31), BVAE_ERR_UNSUPPORTED, "pack_conv_weights: job %d too large", i);
+    jobs.j[i] = PackJob{reinterpret_cast<const float*>(w[i]), wp[i], Cout[i], Cin[i], layout[i], transpose[i]};
+    if (9LL * Cout[i] * Cin[i] > big) big = 9LL * Cout[i] * Cin[i];
+  }
+  int gx = (int)((big + 255) / 256);
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, n);
+  if (dtype == BVAE_F32)
+    pack_conv_batched_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(jobs);
+  else if (dtype == BVAE_BF16)
+    pack_conv_batched_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(jobs);
+  else
+    BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_conv_weights: dtype %d", dtype);
+  BVAE_LAUNCH_CHECK("pack_conv_weights");
   return BVAE_OK;
 }
 

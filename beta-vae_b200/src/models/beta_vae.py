@@ -194,8 +194,39 @@ class BetaVAE(nn.Module):
         b, c, h, w = x.shape
         return x.view(b, h, w, 1) if c == 1 else ops.nchw_to_nhwc(x, F32)
 
+    def _conv_plan(self):
+        """(cache key prefix, conv module, input H, input W, stride) for every encoder / decoder block."""
+        plan = []
+        side = self.cfg.data.image_size
+        for i, blk in enumerate(self.encoder):
+            plan.append((f"encoder.{i}", blk._conv(), side, side, 2))
+            side = ops.conv_out(side, 2)
+        for i, blk in enumerate(self.decoder_blocks):
+            side = side * 2 if blk.upsample else side
+            plan.append((f"decoder_blocks.{i}", blk._conv(), side, side, 1))
+        return plan
+
+    def _prepack(self, dt, in_dt):
+        """Re-make every stale conv weight pack (fprop + dgrad layouts) with ONE kernel launch."""
+        todo = []
+        for idx, (key, conv, H, W, stride) in enumerate(self._conv_plan()):
+            w = conv.weight
+            cout, cin = w.shape[0], w.shape[1]
+            first_dt = dt if (idx > 0 or in_dt == dt) else F32      # the first conv reads the fp32 image
+            lf = ops.conv_weight_layout(H, W, cin, cout, stride, first_dt, 0)
+            lb = ops.conv_weight_layout(H, W, cin, cout, stride, dt, 1)
+            for k, transpose, layout in ((f"{key}.fprop.{lf}", False, lf), (f"{key}.dgrad.{lb}", True, lb)):
+                if not self._packs.valid(k, (w,), dt):
+                    todo.append((k, w, transpose, layout))
+        if todo:
+            with torch.no_grad():
+                outs = ops.pack_conv_many([(w, tr, la) for _, w, tr, la in todo], dt)
+            for (k, w, _, _), o in zip(todo, outs):
+                self._packs.put(k, (w,), dt, o)
+
     def _encode_features(self, x, dt):
         h = self._nhwc_input(x)
+        self._prepack(dt, F32)
         for i, blk in enumerate(self.encoder):
             h = blk(h, self._packs, f"encoder.{i}", dt)
         return h
@@ -214,6 +245,7 @@ class BetaVAE(nn.Module):
         wd, bd = self._packs.get("fc_dec", (self.fc_dec.weight, self.fc_dec.bias), dt,
                                  lambda: ops.pack_fcdec(self.fc_dec.weight, self.fc_dec.bias, dt, c, hs * ws))
         zc = float(self.latent_clamp) if self.latent_clamp is not None else 0.0
+        self._prepack(dt, F32)
         h = ops.FcDec.apply(z, self.fc_dec.weight, self.fc_dec.bias, wd, bd, zc, dt, c, hs, ws)
         for i, blk in enumerate(self.decoder_blocks):
             h = blk(h, self._packs, f"decoder_blocks.{i}", dt)

@@ -56,6 +56,10 @@ unsigned long long bvae_launch_count(void);
  * `transpose` != 0 swaps the roles of ci/co (dgrad: contraction runs over Cout). */
 int bvae_pack_conv_weight(const float* w, void* wp, int Cout, int Cin, int layout, int transpose,
                           int dtype, bvae_stream_t stream);
+/* The same for n <= 32 weights in one launch (host arrays of device pointers / dims): the packs are re-made from
+ * the fp32 masters every training step. */
+int bvae_pack_conv_weights(int n, const void* const* w, void* const* wp, const int* Cout, const int* Cin,
+                           const int* layout, const int* transpose, int dtype, bvae_stream_t stream);
 /* fc_mu / fc_logvar weights [L][C*P] in NCHW-flatten order (beta_vae.py:117-118,138-140)
  * -> one matrix wh[2L][P*C] in NHWC-flatten order (rows 0..L-1 = mu, L..2L-1 = logvar). */
 int bvae_pack_heads_weight(const float* w_mu, const float* w_logvar, void* wh, int L, int C, int P,
