@@ -14,6 +14,7 @@
 // Forward  : stats pass (read y) -> pool pass (read y) -> excite (tiny) -> scale pass (read y, write out)
 // Backward : reduce pass (read dout,y) -> mid (tiny, per sample) -> params (tiny) -> apply pass (read dout,y, write dy)
 #include "common.cuh"
+#include "gn_cluster.cuh"
 
 namespace bvae {
 
@@ -408,6 +409,75 @@ __global__ void __launch_bounds__(256)
                          float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
                          float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int has_se) {
   // job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R].
+  // One thread per job (neighbouring threads read neighbouring addresses); the batch loop runs four
+  // independent accumulator chains so four loads per operand are in flight.
+  const long long n_gb = C, n_w2 = has_se ? (long long)C * R : 0, n_w1 = n_w2, n_b1 = has_se ? R : 0;
+  const long long total = n_gb + n_w2 + n_w1 + n_b1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_gb) {
+      const int c = (int)i;
+      float dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int b0 = 0; b0 < B; b0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + u;
+          if (b < B) {
+            dg[u] += G2[(size_t)b * C + c];
+            db[u] += G1[(size_t)b * C + c];
+            if (has_se) d2[u] += dz2[(size_t)b * C + c];
+          }
+        }
+      }
+      dgamma[c] = (dg[0] + dg[1]) + (dg[2] + dg[3]);
+      dbeta[c] = (db[0] + db[1]) + (db[2] + db[3]);
+      if (has_se) db2[c] = (d2[0] + d2[1]) + (d2[2] + d2[3]);
+    } else if (i < n_gb + n_w2) {
+      const long long k = i - n_gb;
+      const int c = (int)(k / R), j = (int)(k % R);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int b0 = 0; b0 < B; b0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + u;
+          if (b < B) acc[u] = fmaf(dz2[(size_t)b * C + c], hidden[(size_t)b * R + j], acc[u]);
+        }
+      }
+      dw2[k] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    } else if (i < n_gb + n_w2 + n_w1) {
+      const long long k = i - n_gb - n_w2;
+      const int j = (int)(k / C), c = (int)(k % C);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float gc = gamma[c], bc = beta[c];
+      for (int b0 = 0; b0 < B; b0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = b0 + u;
+          if (b < B) {
+            const float pool = (gc * spos[(size_t)b * C + c] + bc * cpos[(size_t)b * C + c]) / (float)P;
+            acc[u] = fmaf(dz1[(size_t)b * R + j], pool, acc[u]);
+          }
+        }
+      }
+      dw1[k] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    } else {
+      const int j = (int)(i - n_gb - n_w2 - n_w1);
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += dz1[(size_t)b * R + j];
+      db1[j] = acc;
+    }
+  }
+}
+
+// Same sums with one WARP per job (lanes over the batch): faster while the job count is small.
+__global__ void __launch_bounds__(256)
+    gn_bwd_params_warp_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
+                         const float* __restrict__ dz1, const float* __restrict__ cpos,
+                         const float* __restrict__ spos, const float* __restrict__ hidden,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
+                         float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int has_se) {
+  // job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R].
   // One WARP per job, lanes stride over the batch (the per-thread serial loop over B was latency bound).
   const long long n_gb = C, n_w2 = has_se ? (long long)C * R : 0, n_w1 = n_w2, n_b1 = has_se ? R : 0;
   const long long total = n_gb + n_w2 + n_w1 + n_b1;
@@ -499,6 +569,26 @@ __global__ void __launch_bounds__(kGnThreads)
   }
 }
 
+static int launch_gn_params(const float* G1, const float* G2, const float* dz2, const float* dz1, const float* cpos,
+                            const float* spos, const float* hidden, const float* gamma, const float* beta,
+                            float* dgamma, float* dbeta, float* dw1, float* db1, float* dw2, float* db2, int B, int P,
+                            int C, int R, bool has_se, cudaStream_t st) {
+  const long long jobs = (long long)C + (has_se ? 2LL * C * R + R : 0);
+  if (jobs <= 32768) {
+    int blocks = (int)((jobs + 7) / 8);  // one warp per job, 8 warps per CTA
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    gn_bwd_params_warp_kernel<<<blocks, 256, 0, st>>>(G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta,
+                                                      dw1, db1, dw2, db2, B, P, C, R, has_se ? 1 : 0);
+  } else {
+    int blocks = (int)((jobs + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    gn_bwd_params_kernel<<<blocks, 256, 0, st>>>(G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1,
+                                                 db1, dw2, db2, B, P, C, R, has_se ? 1 : 0);
+  }
+  BVAE_LAUNCH_CHECK("gn_bwd_params");
+  return BVAE_OK;
+}
+
 // ------------------------------------------------------------------ workspace layout
 struct GnWs {
   double* spart;  // [B][nchunks][2]
@@ -544,6 +634,12 @@ static int gn_fwd_impl(const T* y, T* out, const float* gamma, const float* beta
   BVAE_REQUIRE(gn_geom(P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
                "gn_relu_se: C=%d must be a multiple of %d with C/%d <= 256", C, Vec16<T>::N, Vec16<T>::N);
   GnWs w = gn_ws_carve(ws, B, P, C);
+  {
+    bool handled = false;   // one cluster-resident kernel when the sample fits a cluster's shared memory
+    const int rc = gn_cluster_fwd<T>(y, out, gamma, beta, w1, b1, w2, b2, B, P, C, R, stats, cpos, spos, hidden, gate, st,
+                                     &handled);
+    if (rc != BVAE_OK || handled) return rc;
+  }
   dim3 grid(g.nchunks, B);
   gn_stats_kernel<T><<<grid, g.threads, 0, st>>>(y, w.spart, P, C, g.cv, g.rows, g.pc);
   BVAE_LAUNCH_CHECK("gn_stats");
@@ -573,6 +669,15 @@ static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, con
                "gn_relu_se: C=%d must be a multiple of %d with C/%d <= 256", C, Vec16<T>::N, Vec16<T>::N);
   GnWs w = gn_ws_carve(ws, B, P, C);
   const bool has_se = w1 != nullptr;
+  {
+    bool handled = false;
+    const int rc = gn_cluster_bwd<T>(dout, y, dy, gamma, beta, w1, w2, B, P, C, R, stats, cpos, spos, hidden, gate, w.G1,
+                                     w.G2, w.dz2, w.dz1, st, &handled);
+    if (rc != BVAE_OK) return rc;
+    if (handled)
+      return launch_gn_params(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2,
+                              B, P, C, R, has_se, st);
+  }
   dim3 grid(g.nchunks, B);
   const size_t sm = (size_t)2 * g.rows * C * sizeof(float);
   gn_bwd_reduce_kernel<T><<<grid, g.threads, sm, st>>>(dout, y, stats, gamma, beta, w.p0, w.p1, P, C, g.cv, g.rows,
@@ -582,12 +687,11 @@ static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, con
       w.p0, w.p1, g.nchunks, gamma, beta, w1, w2, cpos, spos, hidden, gate, w.G1, w.G2, w.dz2, w.dz1, w.dpool, w.coef,
       P, C, R);
   BVAE_LAUNCH_CHECK("gn_bwd_mid");
-  const long long jobs = (long long)C + (has_se ? 2LL * C * R + R : 0);
-  int pblocks = (int)((jobs + 7) / 8);  // one warp per job, 8 warps per CTA
-  if (pblocks > 8 * num_sms()) pblocks = 8 * num_sms();
-  gn_bwd_params_kernel<<<pblocks, 256, 0, st>>>(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma,
-                                                dbeta, dw1, db1, dw2, db2, B, P, C, R, has_se ? 1 : 0);
-  BVAE_LAUNCH_CHECK("gn_bwd_params");
+  {
+    const int rc = launch_gn_params(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2,
+                                    db2, B, P, C, R, has_se, st);
+    if (rc != BVAE_OK) return rc;
+  }
   gn_bwd_apply_kernel<T><<<grid, g.threads, 0, st>>>(dout, y, dy, stats, gamma, beta, has_se ? gate : nullptr,
                                                      w.dpool, w.coef, P, C, g.cv, g.rows, g.pc);
   BVAE_LAUNCH_CHECK("gn_bwd_apply");
