@@ -363,53 +363,66 @@ __global__ void __launch_bounds__(256)
 }
 
 // dw[co][ci][t] = sum_split part[split][t][ci][co];  dbias[co] = sum_split bpart[split][co]
-// 64 consecutive elements x 4 split-groups per CTA: coalesced 256-byte rows, four loads in flight per
-// thread and a fixed-order combine in shared memory (deterministic).
-__global__ void __launch_bounds__(256)
+// Many splits (the halo wgrad kernel uses up to one per SM): a CTA of 1024 threads = 64 float4 lanes x 16 split
+// groups covers 256 consecutive elements; every thread keeps four 16-byte loads in flight; fixed-order combine in
+// shared memory (deterministic).  Requires total % 4 == 0 (Cout % 4 == 0).
+__global__ void __launch_bounds__(1024)
     conv_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart, float* __restrict__ dw,
                              float* __restrict__ dbias, int Cin, int Cout, int splits, int bsplits) {
-  __shared__ float sm[4][64];
+  __shared__ float4 sm[16][64];
   const long long total = 9LL * Cin * Cout;
   const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  for (long long base = (long long)blockIdx.x * 64; base < total + Cout; base += (long long)gridDim.x * 64) {
-    const long long i = base + e;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long nblk = (total + 255) / 256;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long i = blk * 256 + 4 * e;
+    float4 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < total) {
       int s = grp;
-      for (; s + 12 < splits; s += 16) {
+      for (; s + 48 < splits; s += 64) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += part[(size_t)(s + 4 * u) * total + i];
+        for (int u = 0; u < 4; ++u) {
+          const float4 v = *reinterpret_cast<const float4*>(part + (size_t)(s + 16 * u) * total + i);
+          acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+        }
       }
-      for (; s < splits; s += 4) acc[0] += part[(size_t)s * total + i];
-    } else if (i < total + Cout && dbias) {
-      const int co = (int)(i - total);
-      for (int s = grp; s < bsplits; s += 4) acc[0] += bpart[(size_t)s * Cout + co];
-    }
-    sm[grp][e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    __syncthreads();
-    if (grp == 0) {
-      const float v = (sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e]);
-      if (i < total) {
-        // i indexes the partial layout [t][ci][co]
-        const int co = (int)(i % Cout);
-        const int ci = (int)((i / Cout) % Cin);
-        const int t = (int)(i / ((long long)Cout * Cin));
-        dw[((size_t)co * Cin + ci) * 9 + t] = v;
-      } else if (i < total + Cout && dbias) {
-        dbias[(int)(i - total)] = v;
+      for (; s < splits; s += 16) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)s * total + i);
+        acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
       }
     }
+    sm[grp][e] = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                             (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
     __syncthreads();
+    if (grp < 4 && i < total) {   // thread (grp, e) finishes component `grp` of lane e's float4
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) v += reinterpret_cast<const float*>(&sm[g][e])[grp];
+      const long long idx = i + grp;
+      const int co = (int)(idx % Cout);
+      const int ci = (int)((idx / Cout) % Cin);
+      const int t = (int)(idx / ((long long)Cout * Cin));
+      dw[((size_t)co * Cin + ci) * 9 + t] = v;
+    }
+    __syncthreads();
+  }
+  if (dbias && blockIdx.x == 0) {
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+      float acc = 0.f;
+      for (int s = 0; s < bsplits; ++s) acc += bpart[(size_t)s * Cout + co];
+      dbias[co] = acc;
+    }
   }
 }
 
 static int launch_wgrad_reduce(const float* part, const float* bpart, float* dw, float* dbias, int Cin, int Cout,
                                int splits, int bsplits, cudaStream_t st) {
   const long long total = 9LL * Cin * Cout + Cout;
-  if (splits >= 8) {
-    long long blocks = (total + 63) / 64;
-    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, splits, bsplits);
+  if (splits >= 8 && Cout % 4 == 0) {
+    long long blocks = (total - Cout + 255) / 256;
+    if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+    conv_wgrad_reduce_kernel<<<(int)blocks, 1024, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, splits, bsplits);
   } else {
     long long blocks = (total + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();

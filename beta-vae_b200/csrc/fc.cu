@@ -180,6 +180,31 @@ static int wide_f_launch(const FcWide& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // grid = B, block = 2L threads (rounded up to a warp multiple): sum the F-chunks, add bias, clamp,
 // reparameterise, per-element KL.
+// out[i] = sum_c part[c][i] (fixed order).  32 elements x 8 chunk groups per CTA, four loads in flight per thread;
+// `out` may alias chunk 0 of `part` (element i is only touched by the CTA that owns it).
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* part, int nchunks, int n, float* out) {
+  __shared__ float sm[8][32];
+  const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i < n) {
+    int c = grp;
+    for (; c + 24 < nchunks; c += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] += part[(size_t)(c + 8 * u) * n + i];
+    }
+    for (; c < nchunks; c += 8) a[0] += part[(size_t)c * n + i];
+  }
+  sm[grp][e] = (a[0] + a[1]) + (a[2] + a[3]);
+  __syncthreads();
+  if (grp == 0 && i < n) {
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += sm[g][e];
+    out[i] = v;
+  }
+}
+
 __global__ void heads_finalize_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ b_mu,
                                       const float* __restrict__ b_lv, const float* __restrict__ eps, float lo,
                                       float hi, int deterministic, float* __restrict__ mu, float* __restrict__ logvar,
@@ -388,7 +413,9 @@ extern "C" int bvae_heads_reparam_kl_fwd(const void* h, const void* wh, const fl
   else
     BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "heads_fwd: dtype %d", dtype);
   if (rc != BVAE_OK) return rc;
-  heads_finalize_kernel<<<B, warp_round(L), 0, st>>>(w.part, cdiv(F, RF_CHUNK), b_mu, b_logvar, eps, lv_lo, lv_hi,
+  chunk_sum_kernel<<<cdiv(B * 2 * L, 32), 256, 0, st>>>(w.part, cdiv(F, RF_CHUNK), B * 2 * L, w.part);
+  BVAE_LAUNCH_CHECK("heads_chunk_sum");
+  heads_finalize_kernel<<<B, warp_round(L), 0, st>>>(w.part, 1, b_mu, b_logvar, eps, lv_lo, lv_hi,
                                                     deterministic, mu, logvar, z, w.kl_elem, lv_pass, B, L);
   BVAE_LAUNCH_CHECK("heads_finalize");
   heads_kl_kernel<<<1, 256, 0, st>>>(w.kl_elem, mu, beta, use_capacity, capacity, capacity_weight, free_bits,
@@ -477,7 +504,9 @@ extern "C" int bvae_fc_dec_bwd(const void* dh0, const float* z, const void* wd, 
                                : reduce_f_launch<__nv_bfloat16>(dh0, wd, w.part, B, L, F, st);
   if (rc != BVAE_OK) return rc;
   const int n = B * L;
-  fcdec_dz_kernel<<<cdiv(n, 256), 256, 0, st>>>(w.part, cdiv(F, RF_CHUNK), z, z_clamp, dz, n);
+  chunk_sum_kernel<<<cdiv(n, 32), 256, 0, st>>>(w.part, cdiv(F, RF_CHUNK), n, w.part);
+  BVAE_LAUNCH_CHECK("fcdec_chunk_sum");
+  fcdec_dz_kernel<<<cdiv(n, 256), 256, 0, st>>>(w.part, 1, z, z_clamp, dz, n);
   BVAE_LAUNCH_CHECK("fcdec_dz");
   // dW[g(f')][l] = sum_b zc[b][l] * dh0[b][f'];  db[g(f')] = sum_b dh0[b][f']  (ones row l == L)
   FcWide p;

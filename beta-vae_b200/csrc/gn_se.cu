@@ -30,7 +30,7 @@ struct GnGeom {
 };
 
 static inline int gn_pixels_per_chunk(int P, int C) {
-  int pc = 16384 / (C > 0 ? C : 1);
+  int pc = 32768 / (C > 0 ? C : 1);
   if (pc < 8) pc = 8;
   if (pc > P) pc = P;
   return pc;
@@ -167,27 +167,51 @@ __global__ void __launch_bounds__(256)
   float* pool = sm;
   float* hid = sm + C;
   const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    // four independent chains keep four loads per array in flight (the serial form is latency bound)
-    double a[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
-    const float* cp = cpart + (size_t)b * nchunks * C + c;
-    const float* xp = xpart + (size_t)b * nchunks * C + c;
-    int k = 0;
-    for (; k + 4 <= nchunks; k += 4) {
+  __shared__ double cs0[256], cs1[256];
+  // chunk sums: thread (c, g) adds chunks g, g+G, ... (G = blockDim / C thread groups when C is small), then a
+  // fixed-order combine -- a single thread per channel walking all chunks is latency bound
+  const int G = (C < (int)blockDim.x) ? (int)blockDim.x / C : 1;
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = (G > 1) ? (int)threadIdx.x % C : c0 + (int)threadIdx.x;
+    const int g = (G > 1) ? (int)threadIdx.x / C : 0;
+    double a = 0.0, q = 0.0;
+    if (c < C && g < G) {
+      const float* cp = cpart + (size_t)b * nchunks * C + c;
+      const float* xp = xpart + (size_t)b * nchunks * C + c;
+      double av[4] = {0.0, 0.0, 0.0, 0.0}, qv[4] = {0.0, 0.0, 0.0, 0.0};
+      int k = g;
+      for (; k + 3 * G < nchunks; k += 4 * G) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a[u] += (double)cp[(size_t)(k + u) * C];
-        q[u] += (double)xp[(size_t)(k + u) * C];
+        for (int u = 0; u < 4; ++u) {
+          av[u] += (double)cp[(size_t)(k + u * G) * C];
+          qv[u] += (double)xp[(size_t)(k + u * G) * C];
+        }
+      }
+      for (; k < nchunks; k += G) {
+        av[0] += (double)cp[(size_t)k * C];
+        qv[0] += (double)xp[(size_t)k * C];
+      }
+      a = (av[0] + av[1]) + (av[2] + av[3]);
+      q = (qv[0] + qv[1]) + (qv[2] + qv[3]);
+    }
+    if (G > 1) {
+      cs0[threadIdx.x] = a;
+      cs1[threadIdx.x] = q;
+      __syncthreads();
+      if (g == 0 && c < C) {
+        for (int gg = 1; gg < G; ++gg) {
+          a += cs0[gg * C + c];
+          q += cs1[gg * C + c];
+        }
       }
     }
-    for (; k < nchunks; ++k) {
-      a[0] += (double)cp[(size_t)k * C];
-      q[0] += (double)xp[(size_t)k * C];
+    if (g == 0 && c < C) {
+      const float as = (float)a, qs = (float)q;
+      cpos[(size_t)b * C + c] = as;
+      spos[(size_t)b * C + c] = qs;
+      pool[c] = (gamma[c] * qs + beta[c] * as) / (float)P;  // mean over pixels of relu(gn(y))
     }
-    const float as = (float)((a[0] + a[1]) + (a[2] + a[3])), qs = (float)((q[0] + q[1]) + (q[2] + q[3]));
-    cpos[(size_t)b * C + c] = as;
-    spos[(size_t)b * C + c] = qs;
-    pool[c] = (gamma[c] * qs + beta[c] * as) / (float)P;  // mean over pixels of relu(gn(y))
+    if (G > 1) break;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -329,32 +353,55 @@ __global__ void __launch_bounds__(256)
   float* dz1 = sm + 3 * C;
   const int b = blockIdx.x;
   const bool has_se = (w1 != nullptr);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double adv[4] = {0.0, 0.0, 0.0, 0.0}, qdv[4] = {0.0, 0.0, 0.0, 0.0};
-    const float* p1 = a1part + (size_t)b * nchunks * C + c;
-    const float* p2 = a2part + (size_t)b * nchunks * C + c;
-    int k = 0;
-    for (; k + 4 <= nchunks; k += 4) {
+  __shared__ double cs0[256], cs1[256];
+  const int G = (C < (int)blockDim.x) ? (int)blockDim.x / C : 1;   // thread groups sharing the chunk loop (see se_excite_kernel)
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = (G > 1) ? (int)threadIdx.x % C : c0 + (int)threadIdx.x;
+    const int g = (G > 1) ? (int)threadIdx.x / C : 0;
+    double ad = 0.0, qd = 0.0;
+    if (c < C && g < G) {
+      const float* p1 = a1part + (size_t)b * nchunks * C + c;
+      const float* p2 = a2part + (size_t)b * nchunks * C + c;
+      double adv[4] = {0.0, 0.0, 0.0, 0.0}, qdv[4] = {0.0, 0.0, 0.0, 0.0};
+      int k = g;
+      for (; k + 3 * G < nchunks; k += 4 * G) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        adv[u] += (double)p1[(size_t)(k + u) * C];
-        qdv[u] += (double)p2[(size_t)(k + u) * C];
+        for (int u = 0; u < 4; ++u) {
+          adv[u] += (double)p1[(size_t)(k + u * G) * C];
+          qdv[u] += (double)p2[(size_t)(k + u * G) * C];
+        }
+      }
+      for (; k < nchunks; k += G) {
+        adv[0] += (double)p1[(size_t)k * C];
+        qdv[0] += (double)p2[(size_t)k * C];
+      }
+      ad = (adv[0] + adv[1]) + (adv[2] + adv[3]);
+      qd = (qdv[0] + qdv[1]) + (qdv[2] + qdv[3]);
+    }
+    if (G > 1) {
+      cs0[threadIdx.x] = ad;
+      cs1[threadIdx.x] = qd;
+      __syncthreads();
+      if (g == 0 && c < C) {
+        for (int gg = 1; gg < G; ++gg) {
+          ad += cs0[gg * C + c];
+          qd += cs1[gg * C + c];
+        }
       }
     }
-    for (; k < nchunks; ++k) {
-      adv[0] += (double)p1[(size_t)k * C];
-      qdv[0] += (double)p2[(size_t)k * C];
+    if (g == 0 && c < C) {
+      const float a = (float)ad, q = (float)qd;
+      A1[c] = a;
+      A2[c] = q;
+      if (has_se) {
+        const float s = gate[(size_t)b * C + c];
+        const float ds = gamma[c] * q + beta[c] * a;
+        const float t = ds * s * (1.f - s);
+        dz2[c] = t;
+        dz2o[(size_t)b * C + c] = t;
+      }
     }
-    const float a = (float)((adv[0] + adv[1]) + (adv[2] + adv[3])), q = (float)((qdv[0] + qdv[1]) + (qdv[2] + qdv[3]));
-    A1[c] = a;
-    A2[c] = q;
-    if (has_se) {
-      const float s = gate[(size_t)b * C + c];
-      const float ds = gamma[c] * q + beta[c] * a;
-      const float t = ds * s * (1.f - s);
-      dz2[c] = t;
-      dz2o[(size_t)b * C + c] = t;
-    }
+    if (G > 1) break;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
