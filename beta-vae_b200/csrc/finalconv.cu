@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(kFcThreads)
 #pragma unroll
       for (int k = 0; k < V; ++k) wacc[t][k] = 0.f;
     float bacc = 0.f;
-    for (long long p = (long long)blockIdx.x * rows + row; p < npix; p += (long long)gridDim.x * rows) {
-      const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+    // 32-bit index arithmetic (host guarantees npix < 2^31): 64-bit div/mod per pixel dominated this loop
+    const int npix32 = (int)npix, pstep = (int)gridDim.x * rows;
+    for (int p = (int)blockIdx.x * rows + row; p < npix32; p += pstep) {
+      const int x = p % W, yb = p / W, y = yb % H, b = yb / H;
       const float* dl = dlogit + ((size_t)b * Co + co) * H * W;
       float d[9];
 #pragma unroll
@@ -161,13 +163,24 @@ __global__ void __launch_bounds__(kFcThreads)
       if (dh) {
         Vec16<T> o;
         if (co > 0) o.load(dh + off);
+        float a[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          float a = co > 0 ? o.v[k] : 0.f;
+        for (int k = 0; k < V; ++k) a[k] = co > 0 ? o.v[k] : 0.f;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(d[t], wsm[(co * 9 + t) * C + col * V + k], a);
-          o.v[k] = a;
+        for (int t = 0; t < 9; ++t) {
+          // 16-byte shared-memory reads (the scalar form made this loop LDS-issue bound)
+          const float4* wq = reinterpret_cast<const float4*>(wsm + (co * 9 + t) * C + col * V);
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const float4 w4 = wq[q];
+            a[4 * q] = fmaf(d[t], w4.x, a[4 * q]);
+            a[4 * q + 1] = fmaf(d[t], w4.y, a[4 * q + 1]);
+            a[4 * q + 2] = fmaf(d[t], w4.z, a[4 * q + 2]);
+            a[4 * q + 3] = fmaf(d[t], w4.w, a[4 * q + 3]);
+          }
         }
+#pragma unroll
+        for (int k = 0; k < V; ++k) o.v[k] = a[k];
         o.store(dh + off);
       }
     }
@@ -196,21 +209,36 @@ __global__ void __launch_bounds__(kFcThreads)
 }
 
 // dw[co][c][t] = sum_cta wpart[cta][co][t][c];  db[co] = sum_cta bpart[cta][co]
+// 32 elements x 8 CTA-groups per block, four loads in flight per thread, fixed-order combine.
 __global__ void __launch_bounds__(256)
     finalconv_wreduce_kernel(const float* __restrict__ wpart, const float* __restrict__ bpart, float* __restrict__ dw,
                              float* __restrict__ db, int nctas, int C, int Co) {
+  __shared__ float sm[8][32];
   const int total = Co * 9 * C;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + Co; i += gridDim.x * blockDim.x) {
+  const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i < total + Co) {
+    const float* src = i < total ? wpart + i : bpart + (i - total);
+    const size_t stride = i < total ? (size_t)total : (size_t)Co;
+    int k = grp;
+    for (; k + 24 < nctas; k += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] += src[(size_t)(k + 8 * u) * stride];
+    }
+    for (; k < nctas; k += 8) a[0] += src[(size_t)k * stride];
+  }
+  sm[grp][e] = (a[0] + a[1]) + (a[2] + a[3]);
+  __syncthreads();
+  if (grp == 0 && i < total + Co) {
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += sm[g][e];
     if (i < total) {
       const int c = i % C, t = (i / C) % 9, co = i / (9 * C);
-      float a = 0.f;
-      for (int k = 0; k < nctas; ++k) a += wpart[(size_t)k * total + i];
-      dw[((size_t)co * C + c) * 9 + t] = a;
+      dw[((size_t)co * C + c) * 9 + t] = v;
     } else {
-      const int co = i - total;
-      float a = 0.f;
-      for (int k = 0; k < nctas; ++k) a += bpart[(size_t)k * Co + co];
-      db[co] = a;
+      db[i - total] = v;
     }
   }
 }
@@ -323,10 +351,11 @@ static int final_bwd_impl(const void* h, const float* w, const float* recon, con
   BVAE_LAUNCH_CHECK("dlogit");
   const size_t sm = ((size_t)Co * 9 * C + (size_t)g.rows * C) * sizeof(float);
   BVAE_REQUIRE(sm <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "finalconv: C=%d too large", C);
+  BVAE_REQUIRE((long long)B * H * W < (1LL << 31) - 65536 * 1024LL, BVAE_ERR_UNSUPPORTED, "finalconv_bwd: too many pixels");
   finalconv_bwd_kernel<T><<<g.ctas, g.threads, sm, st>>>((const T*)h, w, fw.dlogit, (T*)dh, fw.wpart, fw.bpart, B, H,
                                                          W, C, Co, g.cv);
   BVAE_LAUNCH_CHECK("finalconv_bwd");
-  finalconv_wreduce_kernel<<<cdiv(Co * 9 * C + Co, 256), 256, 0, st>>>(fw.wpart, fw.bpart, dw, db, g.ctas, C, Co);
+  finalconv_wreduce_kernel<<<cdiv(Co * 9 * C + Co, 32), 256, 0, st>>>(fw.wpart, fw.bpart, dw, db, g.ctas, C, Co);
   BVAE_LAUNCH_CHECK("finalconv_wreduce");
   return BVAE_OK;
 }
