@@ -430,3 +430,36 @@ class FinalConvSigmoidRecon(torch.autograd.Function):
             call("bvae_finalconv_sigmoid_recon_bwd", _p(h), _p(w), _p(recon), _p(target), _p(g_recon), _p(g_loss),
                  _p(dh), _p(dw), _p(db), ctx.loss_type, _p(ws), ws.numel(), B, H, W, Cc, Co, code_of(h), _stream())
         return dh, dw, db, None, None
+
+
+class FocalFrequencyCore(torch.autograd.Function):
+    """Spectrum-side arithmetic of the focal-frequency loss (src/training/losses.py:23-33) on the one-sided rfft2
+    spectrum, passed as its real view [B, C, H, W/2+1, 2]."""
+
+    @staticmethod
+    def forward(ctx, spec_ri, W, alpha, eps):
+        B, Cc, H, Wh, two = spec_ri.shape
+        assert two == 2 and Wh == W // 2 + 1
+        spec_ri = spec_ri.contiguous()
+        dev = spec_ri.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        scale = torch.empty(Cc, dtype=torch.float32, device=dev)
+        U = torch.empty(Cc, dtype=torch.float32, device=dev)
+        ws = _ws(query("bvae_ffl_workspace", Cc), dev)
+        with profiler.region("ffl_fwd", nbytes=2.0 * spec_ri.numel() * 4):
+            call("bvae_ffl_fwd", _p(spec_ri), B, Cc, H, Wh, W, float(alpha), float(eps), _p(loss), _p(scale), _p(U),
+                 _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(spec_ri, scale, U)
+        ctx.cfg = (W, float(alpha), float(eps))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        spec_ri, scale, U = ctx.saved_tensors
+        W, alpha, eps = ctx.cfg
+        B, Cc, H, Wh, _ = spec_ri.shape
+        g = torch.empty_like(spec_ri)
+        g_loss = g_loss.contiguous().float()
+        with profiler.region("ffl_bwd", nbytes=2.0 * spec_ri.numel() * 4):
+            call("bvae_ffl_bwd", _p(spec_ri), _p(scale), _p(U), _p(g_loss), _p(g), B, Cc, H, Wh, W, alpha, eps, _stream())
+        return g, None, None, None

@@ -1,10 +1,12 @@
 """Auxiliary reconstruction losses -- drop-in for the reference's ``training.losses``
 (reference: src/training/losses.py:5-75).
 
-FocalFrequencyLoss is on the default config's loss path (weight 0.5) but is not one of the
-subsystems BASELINE.json's north_star names; it stays a device-side torch.fft composition
-("next" row 2).  Its gradient reaches the fused final-conv kernel through
-the ``recon`` output of ``ops.FinalConvSigmoidRecon``.
+FocalFrequencyLoss is on the default config's loss path (weight 0.5).  The transform is cuFFT
+(``torch.fft.rfft2`` of the difference image: the FFT is linear, so F(pred) - F(target) =
+F(pred - target)); everything after it -- |F|^2, the batch-mean scale, the focal weight, the mean and
+their backward -- is ``ops.FocalFrequencyCore`` (bvae_ffl_fwd / bvae_ffl_bwd), four launches instead of
+about twenty-five.  Its gradient reaches the fused final-conv kernel through the ``recon`` output of
+``ops.FinalConvSigmoidRecon``.  CPU tensors take the plain torch composition (stand-alone use only).
 LPIPS is a third-party AlexNet (package + weights unavailable offline): out of scope."""
 import torch
 import torch.nn as nn
@@ -22,6 +24,11 @@ class FocalFrequencyLoss(nn.Module):
     def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if pred.shape != target.shape:
             raise ValueError(f"Shape mismatch: pred {pred.shape} vs target {target.shape}")
+        if pred.is_cuda:
+            from bvae_rt import ops
+            with torch.amp.autocast("cuda", enabled=False):
+                spec = torch.fft.rfft2(pred.float() - target.float(), norm="ortho")
+                return ops.FocalFrequencyCore.apply(torch.view_as_real(spec), pred.shape[-1], self.alpha, self.eps)
         with torch.amp.autocast("cuda", enabled=False):
             spec = torch.fft.fft2(pred.float(), norm="ortho") - torch.fft.fft2(target.float(), norm="ortho")
             power = spec.real.square() + spec.imag.square()

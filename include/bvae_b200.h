@@ -192,6 +192,19 @@ int bvae_adam_clip_step_dev(float* p, const float* g, float* m, float* v, size_t
                             float grad_scale, float max_norm, const float* hyper, float beta1, float beta2,
                             float eps, float weight_decay, int decoupled_wd, bvae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Focal-frequency loss, spectrum side (FocalFrequencyLoss.forward, src/training/losses.py:23-33, without the
+ * FFT itself): spec = one-sided rfft2 of (pred - target), [B][C][H][Wh = W/2+1] interleaved (re, im) fp32.
+ *   loss[0] = mean(w * |F|^2),  w = clamp_min(|F|^2 / scale_c, eps)^alpha,  scale_c = mean_{n,h,w} |F|^2 + eps
+ * scale [C] and U [C] are saved for the backward, which returns the gradient w.r.t. the complex spectrum
+ * (PyTorch convention: d/dre + i d/dim), g_loss = upstream gradient of the scalar (device).
+ * ---------------------------------------------------------------------------------------- */
+size_t bvae_ffl_workspace(int C);
+int bvae_ffl_fwd(const float* spec, int B, int C, int H, int Wh, int W, float alpha, float eps, float* loss,
+                 float* scale, float* U, void* ws, size_t ws_bytes, bvae_stream_t stream);
+int bvae_ffl_bwd(const float* spec, const float* scale, const float* U, const float* g_loss, float* g_spec, int B,
+                 int C, int H, int Wh, int W, float alpha, float eps, bvae_stream_t stream);
+
 /* NCHW fp32 -> NHWC act dtype (RGB input path, data.grayscale: false) and back. */
 int bvae_nchw_to_nhwc(const float* x, void* y, int B, int C, int H, int W, int dtype, bvae_stream_t stream);
 

@@ -388,3 +388,31 @@ def test_errors_are_loud():
         ops.conv3x3_fprop(x, wp, None, 8, 1, ops.F32)
     with pytest.raises(BvaeError):
         ops.upsample2x_fwd(torch.zeros(1, 2, 2, 8))       # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5, 2.0])
+@pytest.mark.parametrize("shape", [(4, 1, 32, 32), (2, 3, 16, 24), (3, 1, 8, 9), (32, 1, 128, 128)])
+def test_focal_frequency_loss_core(shape, alpha):
+    """FocalFrequencyLoss on CUDA (rfft2 + bvae_ffl_*) against the reference composition (fft2 of both images,
+    src/training/losses.py:23-33) in fp64, values and gradient."""
+    from training.losses import FocalFrequencyLoss
+    g = torch.Generator().manual_seed(sum(shape))
+    pred = torch.rand(shape, generator=g)
+    target = torch.rand(shape, generator=g)
+    if shape[0] == 3:
+        pred[0] = target[0]                    # an image with zero difference: exercises the clamp_min branch
+
+    def ref(p, t, eps=1e-8):
+        spec = torch.fft.fft2(p, norm="ortho") - torch.fft.fft2(t, norm="ortho")
+        power = spec.real.square() + spec.imag.square()
+        scale = power.mean(dim=(0, 2, 3), keepdim=True) + eps
+        return ((power / scale).clamp_min(eps).pow(alpha) * power).mean()
+
+    pr = pred.double().requires_grad_(True)
+    want = ref(pr, target.double())
+    want.backward()
+    pd = pred.to(dev()).requires_grad_(True)
+    got = FocalFrequencyLoss(alpha=alpha)(pd, target.to(dev()))
+    (got * 1.7).backward()
+    assert rel_err(got, want) <= 2e-5
+    assert rel_err(pd.grad / 1.7, pr.grad) <= 5e-5
