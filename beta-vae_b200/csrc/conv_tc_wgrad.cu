@@ -165,33 +165,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------
-// Stride-1 wgrad, halo formulation (same idea as conv_tc_halo.cu): per 16x8-pixel tile ONE TMA box
-// brings the (18 x 10 pixel) x 64-channel x halo, and the nine taps are shifted MN-major windows of it
-// (start = window offset, 8-pixel atoms one halo row = 1280 B apart).  A CTA owns one
-// (64 input channels) x (64 output channels) block of dW for ALL nine taps -- five 128-row
-// accumulators in TMEM: taps (0,1) (2,3) (4,5) (6,7) (8, ones) -- and walks its share of the pixel
-// tiles (split-K over tiles).  The spare half of the fifth accumulator multiplies an all-ones A
-// block with the dy tile, i.e. it is the bias gradient: no separate column-sum pass over dy.
-// Per tile: 23 KB of x + 16 KB of dy for 40 MMAs (128x64x16) = ~30 B per tensor-core cycle.
+// wgrad, halo formulation (same idea as conv_tc_halo.cu).  Per (th x 8)-pixel output tile the input arrives
+// as ONE TMA box per source plane and the nine taps are shifted MN-major windows of those buffers
+// (start = window offset, 8-pixel atoms one buffer row apart):
+//   stride 1: one plane, box (th+2) x 10 pixels x 64 channels, rows 1280 B apart;
+//   stride 2: the four parity planes x[2i+ph][2j+pw] (plain strided tensor maps), each a (th+1) x 9 box with rows
+//             1152 B apart; tap (r, s) reads plane ((r != 1), (s != 1)) at row / column offset (r != 0), (s != 0).
+// A CTA owns one (64 input channels) x (64 output channels) block of dW for ALL nine taps -- five 128-row
+// accumulators in TMEM, two taps each, paired in increasing window address so the second tap is reached through the
+// descriptor's leading-dimension offset -- and walks its share of the pixel tiles (split-K over tiles).  The spare
+// half of the fifth accumulator multiplies an all-ones A block with the dy tile, i.e. it is the bias gradient: no
+// separate column-sum pass over dy.  Per stride-1 tile: 23 KB of x + 16 KB of dy for 40 MMAs (128x64x16).
 // ------------------------------------------------------------------------------------------
-static constexpr uint32_t WH_HALO_SLOT = 24576, WH_DY_BYTES = 16384, WH_STAGE = WH_HALO_SLOT + WH_DY_BYTES;
-static constexpr uint32_t WH_HALO_BYTES = 18 * 10 * 128, WH_ROWSTRIDE = 1280, WH_ONES_BYTES = 2560;
+static constexpr uint32_t WH_ONES_BYTES = 2560;
 
 struct WgHaloParams {
   int cin_chunks, co_blocks;
   int tiles_w, tiles_h, m_tiles, tiles_per_split;
   int Cin, Cout;
-  int stages;
+  int stages, nplanes, th, ksteps;
+  uint32_t slot_bytes;      // one plane buffer (padded to 1024)
+  uint32_t box_bytes;       // bytes TMA delivers per plane
+  uint32_t dy_bytes;        // th * 8 * 128
+  uint32_t stage_bytes;     // nplanes * slot_bytes + dy_bytes
+  uint32_t sbo;             // bytes between 8-pixel atoms of a window = one buffer row
+  uint32_t win[10];         // byte offset of accumulator-slot position q's window inside a stage (q = 2*rb + half)
+  int tap[10];              // weight tap (r*3+s) held at position q; position 9 = the ones block (bias gradient)
   uint32_t ones_off, bar_off;
   float* part;   // [split][9][Cin][Cout]
   float* bpart;  // [split][Cout] or null
 };
 struct WgHaloMaps {
-  CUtensorMap x, dy;
+  CUtensorMap x[4], dy;
 };
 
-__device__ __forceinline__ constexpr uint32_t wh_win(int j) { return (uint32_t)((j / 3) * 10 + (j % 3)) * 128u; }
-
+template <int KSTEPS>
 __global__ void __launch_bounds__(WG_THREADS, 1)
     conv_wgrad_halo_kernel(const __grid_constant__ WgHaloMaps maps, const WgHaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -226,20 +234,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
   if (warp == 0) {
     if (lane == 0) {
-      tma_prefetch_desc(&maps.x);
+      for (int q = 0; q < p.nplanes; ++q) tma_prefetch_desc(&maps.x[q]);
       tma_prefetch_desc(&maps.dy);
+      int st = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int st = it % p.stages;
-        mbar_wait(&empty_bar[st], (((uint32_t)(it / p.stages)) & 1u) ^ 1u);
+        mbar_wait(&empty_bar[st], ph ^ 1u);
         int tile = t_beg + it;
         const int w0 = (tile % p.tiles_w) * 8;
         tile /= p.tiles_w;
-        const int h0 = (tile % p.tiles_h) * 16;
+        const int h0 = (tile % p.tiles_h) * p.th;
         const int b = tile / p.tiles_h;
-        uint8_t* base = smem + (size_t)st * WH_STAGE;
-        mbar_expect_tx(&full_bar[st], WH_HALO_BYTES + WH_DY_BYTES);
-        tma_load_4d(&maps.x, &full_bar[st], base, cc * 64, w0 - 1, h0 - 1, b);
-        tma_load_4d(&maps.dy, &full_bar[st], base + WH_HALO_SLOT, cb * 64, w0, h0, b);
+        uint8_t* base = smem + (size_t)st * p.stage_bytes;
+        mbar_expect_tx(&full_bar[st], (uint32_t)p.nplanes * p.box_bytes + p.dy_bytes);
+        for (int q = 0; q < p.nplanes; ++q)
+          tma_load_4d(&maps.x[q], &full_bar[st], base + (size_t)q * p.slot_bytes, cc * 64, w0 - 1, h0 - 1, b);
+        tma_load_4d(&maps.dy, &full_bar[st], base + (size_t)p.nplanes * p.slot_bytes, cb * 64, w0, h0, b);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -248,52 +259,59 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                  ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint64_t dconst = (1ull << 46) | (2ull << 61);
-      constexpr uint64_t a_sbo = (uint64_t)(WH_ROWSTRIDE >> 4) << 32;
+      const uint64_t a_sbo = (uint64_t)(p.sbo >> 4) << 32;
       constexpr uint64_t b_fixed = dconst | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
-      const uint32_t ones_addr = smem_u32(smem + p.ones_off);
+      // Everything that does not depend on the stage is folded into five 64-bit descriptor bases up front; the
+      // tile loop then issues its 5 x KSTEPS MMAs with one add each (the issuing thread's scalar latency is what
+      // bounds a loop like this -- see conv_tc_halo.cu).
+      const uint32_t ones16 = smem_u32(smem + p.ones_off) >> 4;
+      const uint32_t ks16 = (2u * p.sbo) >> 4;            // 16 pixels = two tile rows per K step
+      const uint32_t win8_16 = p.win[8] >> 4;
+      uint64_t abase[5];
+#pragma unroll
+      for (int rb = 0; rb < 5; ++rb) {
+        const uint64_t lbo = rb < 4 ? (uint64_t)((p.win[2 * rb + 1] - p.win[2 * rb]) >> 4) << 16 : 0ull;
+        abase[rb] = dconst | a_sbo | lbo | (uint64_t)(p.win[2 * rb] >> 4);
+      }
+      int st = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int st = it % p.stages;
-        mbar_wait(&full_bar[st], ((uint32_t)(it / p.stages)) & 1u);
+        mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + (size_t)st * WH_STAGE);
-        const uint64_t a_lo = (uint64_t)(a0 >> 4);
-        const uint64_t b_desc0 = b_fixed | (uint64_t)((a0 + WH_HALO_SLOT) >> 4);
+        const uint32_t a0 = smem_u32(smem + (size_t)st * p.stage_bytes);
+        const uint32_t a16 = a0 >> 4;
+        const uint64_t b_desc0 = b_fixed | (uint64_t)((a0 + (uint32_t)p.nplanes * p.slot_bytes) >> 4);
         const uint32_t acc_on = it != 0 ? 1u : 0u;
 #pragma unroll
         for (int rb = 0; rb < 5; ++rb) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const uint32_t win = wh_win(2 * rb);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            uint64_t lbo;
-            if (rb < 4)
-              lbo = (uint64_t)((wh_win(2 * rb + 1) - wh_win(2 * rb)) >> 4) << 16;
-            else
-              lbo = (uint64_t)((ones_addr - (a0 + win + (uint32_t)k * 2u * WH_ROWSTRIDE)) >> 4) << 16;
-            const uint64_t adesc = (dconst | a_sbo | lbo) + a_lo + (uint64_t)((win + (uint32_t)k * 2u * WH_ROWSTRIDE) >> 4);
-            umma_bf16(tmem_base + (uint32_t)(rb * 64), adesc, b_desc0 + (uint64_t)((k * 2048) >> 4), idesc,
-                      k != 0 ? 1u : acc_on);
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint32_t addr16 = a16 + (uint32_t)k * ks16;
+            uint64_t adesc = abase[rb] + (uint64_t)addr16;
+            // fifth accumulator: the second 64-row half is the all-ones block (bias gradient)
+            if (rb == 4) adesc |= (uint64_t)((ones16 - (win8_16 + addr16)) & 0x3FFFu) << 16;
+            umma_bf16(tmem_base + (uint32_t)(rb * 64), adesc, b_desc0 + (uint64_t)(k * 128), idesc, k != 0 ? 1u : acc_on);
           }
         }
         umma_commit(&empty_bar[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
       umma_commit(accum_bar);
     }
   } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;  // accumulator row: tap half (m / 64), input channel (m % 64)
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;  // accumulator row: slot half (m / 64), input channel (m % 64)
     mbar_wait(accum_bar, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int rb = 0; rb < 5; ++rb) {
-      const int tap = 2 * rb + (m >> 6);
+      const int pos = 2 * rb + (m >> 6);
       float* out = nullptr;
-      if (tap < 9)
-        out = p.part + (((size_t)split * 9 + tap) * p.Cin + (size_t)cc * 64 + (m & 63)) * p.Cout + (size_t)cb * 64;
+      if (pos < 9)
+        out = p.part + (((size_t)split * 9 + p.tap[pos]) * p.Cin + (size_t)cc * 64 + (m & 63)) * p.Cout + (size_t)cb * 64;
       else if (m == 64 && cc == 0 && p.bpart)
         out = p.bpart + (size_t)split * p.Cout + (size_t)cb * 64;   // ones-row: sum over pixels of dy
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(rb * 64);
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
@@ -314,49 +332,93 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
 static bool wgrad_halo_ok(int H, int W, int Cin, int Cout, int stride) {
   if (getenv("BVAE_CONV_NO_HALO")) return false;
-  return stride == 1 && H % 16 == 0 && W % 8 == 0 && Cin % 64 == 0 && Cout % 64 == 0;
+  if (Cin % 64 || Cout % 64) return false;
+  if (stride == 2 && ((H | W) & 1)) return false;
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+  return (stride == 1 || stride == 2) && OH % 8 == 0 && OW % 8 == 0;
 }
+static int wgrad_halo_th(int OH) { return OH % 16 == 0 ? 16 : 8; }
 
 static int conv_wgrad_halo(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
-                           int W, int Cin, int Cout, cudaStream_t st) {
+                           int W, int Cin, int Cout, int stride, cudaStream_t st) {
   WgHaloMaps maps;
   WgHaloParams p;
   memset(&p, 0, sizeof(p));
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+  p.th = wgrad_halo_th(OH);
+  p.ksteps = p.th / 2;
   p.cin_chunks = Cin / 64;
   p.co_blocks = Cout / 64;
-  p.tiles_w = W / 8;
-  p.tiles_h = H / 16;
+  p.tiles_w = OW / 8;
+  p.tiles_h = OH / p.th;
   p.m_tiles = pl.tiles_total;
   p.tiles_per_split = pl.tiles_per_split;
   p.Cin = Cin; p.Cout = Cout;
-  p.stages = 5;
-  p.ones_off = (uint32_t)p.stages * WH_STAGE;
-  p.bar_off = p.ones_off + 3072;
   p.part = part;
   p.bpart = bpart;
-  {
+  p.dy_bytes = (uint32_t)p.th * 8 * 128;
+  uint32_t bw, bh;   // plane box: pixels per row, rows
+  if (stride == 1) {
+    p.nplanes = 1; bw = 10; bh = (uint32_t)p.th + 2;
+    for (int j = 0; j < 9; ++j) {
+      p.win[j] = (uint32_t)((j / 3) * 10 + (j % 3)) * 128u;
+      p.tap[j] = j;
+    }
+  } else {
+    p.nplanes = 4; bw = 9; bh = (uint32_t)p.th + 1;
+  }
+  p.sbo = bw * 128;
+  p.box_bytes = bw * bh * 128;
+  p.slot_bytes = (uint32_t)align_up(p.box_bytes, 1024);
+  p.stage_bytes = (uint32_t)p.nplanes * p.slot_bytes + p.dy_bytes;
+  if (stride == 2) {
+    // taps sorted by window address: plane slot q = ph*2+pw with ph = (r != 1), pw = (s != 1); row/col offset (r != 0), (s != 0)
+    static const int order[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
+    for (int pos = 0; pos < 9; ++pos) {
+      const int t = order[pos], r = t / 3, s = t % 3;
+      const int q = (r != 1 ? 2 : 0) + (s != 1 ? 1 : 0);
+      p.win[pos] = (uint32_t)q * p.slot_bytes + (uint32_t)((r != 0 ? 1 : 0) * (int)bw + (s != 0 ? 1 : 0)) * 128u;
+      p.tap[pos] = t;
+      if (pos > 0) BVAE_REQUIRE(p.win[pos] > p.win[pos - 1], BVAE_ERR_UNSUPPORTED, "conv_wgrad_halo: window order");
+    }
+  }
+  p.win[9] = 0;
+  p.tap[9] = -1;
+  const size_t budget = 226 * 1024 - 1024 - 4096;
+  int stages = (int)(budget / p.stage_bytes);
+  p.stages = stages > 5 ? 5 : stages;
+  BVAE_REQUIRE(p.stages >= 2, BVAE_ERR_UNSUPPORTED, "conv_wgrad_halo: stage of %u bytes does not fit twice", p.stage_bytes);
+  p.ones_off = (uint32_t)p.stages * p.stage_bytes;
+  p.bar_off = p.ones_off + 3072;
+  const uint32_t xbox[4] = {64u, bw, bh, 1u};
+  if (stride == 1) {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    const uint32_t box[4] = {64u, 10u, 18u, 1u};
-    int rc = make_map(&maps.x, x, 4, dims, strides, box, 128);
+    int rc = make_map(&maps.x[0], x, 4, dims, strides, xbox, 128);
     if (rc) return rc;
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        const char* base = reinterpret_cast<const char*>(x) + ((size_t)ph * W + pw) * Cin * 2;
+        int rc = make_map(&maps.x[ph * 2 + pw], base, 4, dims, strides, xbox, 128);
+        if (rc) return rc;
+      }
   }
   {
-    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-    const uint32_t box[4] = {64u, 8u, 16u, 1u};
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)OW * Cout * 2, (uint64_t)OH * OW * Cout * 2};
+    const uint32_t box[4] = {64u, 8u, (uint32_t)p.th, 1u};
     int rc = make_map(&maps.dy, dy, 4, dims, strides, box, 128);
     if (rc) return rc;
   }
   const size_t smem = 1024 + p.bar_off + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad_halo: cudaFuncSetAttribute");
-    configured = true;
-  }
+  auto kern = p.ksteps == 8 ? conv_wgrad_halo_kernel<8> : conv_wgrad_halo_kernel<4>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad_halo: cudaFuncSetAttribute");
   dim3 grid(p.cin_chunks * p.co_blocks, pl.splits);
-  conv_wgrad_halo_kernel<<<grid, WG_THREADS, smem, st>>>(maps, p);
+  kern<<<grid, WG_THREADS, smem, st>>>(maps, p);
   BVAE_LAUNCH_CHECK("conv_wgrad_halo");
   return BVAE_OK;
 }
@@ -404,7 +466,10 @@ WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int strid
   WgradTcPlan pl;
   if (wgrad_halo_ok(H, W, Cin, Cout, stride)) {
     pl.bn = 64; pl.slots = 5; pl.groups = (Cin / 64) * (Cout / 64);
-    pl.tiles_total = B * (H / 16) * (W / 8);
+    {
+      const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+      pl.tiles_total = B * (OH / wgrad_halo_th(OH)) * (OW / 8);
+    }
     int splits = num_sms() / pl.groups;
     if (splits < 1) splits = 1;
     if (splits > pl.tiles_total) splits = pl.tiles_total;
@@ -455,7 +520,7 @@ WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int strid
 
 int conv_tc_wgrad(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
                   int W, int Cin, int Cout, int stride, cudaStream_t st) {
-  if (wgrad_halo_ok(H, W, Cin, Cout, stride)) return conv_wgrad_halo(x, dy, part, bpart, pl, B, H, W, Cin, Cout, st);
+  if (wgrad_halo_ok(H, W, Cin, Cout, stride)) return conv_wgrad_halo(x, dy, part, bpart, pl, B, H, W, Cin, Cout, stride, st);
   WgMaps maps;
   WgParams p;
   memset(&p, 0, sizeof(p));

@@ -81,6 +81,12 @@ CONV_SHAPES = [
     (3, 16, 16, 512, 256, 1),   # streamed weights, 8 K chunks, TM=1
     (40, 32, 32, 256, 128, 1),  # streamed weights shared by TM=2 pixel tiles
     (239, 16, 8, 128, 128, 1),  # TM=2 with an odd number of tiles (last unit half empty)
+    # halo wgrad on the four stride-2 parity planes / 8-row tiles
+    (4, 64, 64, 64, 128, 2),
+    (3, 32, 32, 128, 256, 2),
+    (2, 16, 16, 256, 512, 2),
+    (3, 8, 8, 64, 64, 1),
+    (2, 24, 40, 64, 64, 1),
 ]
 
 
