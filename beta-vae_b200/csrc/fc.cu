@@ -106,14 +106,25 @@ struct FcWide {
 
 static constexpr int WF_MT = 32, WF_FT = 128, WF_KT = 16;
 
+// With the NHWC -> NCHW feature permutation (permC > 0: the weight-gradient outputs, reference layout [..][C*P]) a
+// CTA's 128 features are a (16 pixels x 8 channels) patch when P % 16 == 0 and C % 8 == 0: Bm is read as 16-byte
+// channel runs, and every thread stores four consecutive pixels of one channel -- 16 contiguous bytes -- instead of
+// four 4-byte stores P floats apart.  Otherwise the tile is 128 consecutive features.
 template <typename TB, typename TO>
 __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
   __shared__ __align__(16) float As[WF_KT][WF_MT + 4];
   __shared__ __align__(16) float Bs[WF_KT][WF_FT + 4];
   const TB* __restrict__ Bm = reinterpret_cast<const TB*>(p.Bm);
   const int tid = threadIdx.x;
+  const bool patch = p.permC > 0 && p.permP % 16 == 0 && p.permC % 8 == 0;
   const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * WF_MT;
-  const int ty = tid >> 5, tx = tid & 31;  // rows ty*4..+3, features tx*4..+3
+  int pc0 = 0, pp0 = 0;                       // patch origin (channel, pixel)
+  if (patch) {
+    const int ctiles = p.permC / 8;
+    pc0 = (blockIdx.x % ctiles) * 8;
+    pp0 = (blockIdx.x / ctiles) * 16;
+  }
+  const int ty = tid >> 5, tx = tid & 31;  // rows ty*4..+3, tile-local features tx*4..+3
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -130,10 +141,17 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
       As[k][m] = v;
     }
     for (int i = tid; i < WF_KT * WF_FT; i += 256) {
-      const int k = i / WF_FT, f = i % WF_FT;
+      const int k = i / WF_FT, fl = i % WF_FT;
       float v = 0.f;
-      if (k0 + k < p.K && f0 + f < p.F) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + f0 + f]);
-      Bs[k][f] = v;
+      if (patch) {
+        // memory order: channel fastest (8-channel runs); tile-local order: pixel fastest within a channel
+        const int cl = fl & 7, pl = fl >> 3;
+        if (k0 + k < p.K) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + (size_t)(pp0 + pl) * p.permC + pc0 + cl]);
+        Bs[k][cl * 16 + pl] = v;
+      } else {
+        if (k0 + k < p.K && f0 + fl < p.F) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + f0 + fl]);
+        Bs[k][fl] = v;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -147,6 +165,40 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
   }
+  if (p.o0_sm == 1) {
+    // output is row-contiguous in m (fc_dec dW [F][L]): stage the tile in shared memory and let each warp write one
+    // feature's 32 rows as one 128-byte segment
+    __shared__ float Cs[WF_FT][WF_MT + 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Cs[tx * 4 + j][ty * 4 + i] = acc[i][j];
+    __syncthreads();
+    const int m = m0 + tx;   // lane = row
+    for (int fl = ty; fl < WF_FT; fl += 8) {
+      long long g;
+      long long fsrc;        // NHWC feature index (bias lookup)
+      if (patch) {
+        const int c = pc0 + (fl >> 4), px = pp0 + (fl & 15);
+        g = (long long)c * p.permP + px;
+        fsrc = (long long)px * p.permC + c;
+      } else {
+        const int f = f0 + fl;
+        if (f >= p.F) continue;
+        g = p.permC > 0 ? (long long)(f % p.permC) * p.permP + f / p.permC : f;
+        fsrc = f;
+      }
+      if (m >= p.M) continue;
+      const bool lo = m < p.split;
+      TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
+      const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
+      const long long mm = lo ? m : m - p.split;
+      float v = Cs[fl][tx];
+      if (p.bias) v += p.bias[fsrc];
+      base[mm * sm + g * sf] = Elem<TO>::from_f(v);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -155,6 +207,21 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
     TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
     const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
     const long long mm = lo ? m : m - p.split;
+    if (patch) {
+      // tile-local features tx*4..+3 = channel pc0 + tx/4, pixels pp0 + (tx%4)*4 .. +3  ->  g = c*P + pixel
+      const int c = pc0 + (tx >> 2), px = pp0 + (tx & 3) * 4;
+      const long long g = (long long)c * p.permP + px;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + (p.bias ? p.bias[(size_t)(px + j) * p.permC + c] : 0.f);
+      if (sf == 1 && sizeof(TO) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + mm * sm + g) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) base[mm * sm + (g + j) * sf] = Elem<TO>::from_f(v[j]);
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int f = f0 + tx * 4 + j;
