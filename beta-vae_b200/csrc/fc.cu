@@ -36,7 +36,24 @@ __global__ void __launch_bounds__(256) fc_reduce_f_kernel(const T* __restrict__ 
   const int chunk = blockIdx.x, m0 = blockIdx.y * RF_MT;
   const int f0 = chunk * RF_CHUNK;
   const int tid = threadIdx.x;
+  // 16-byte loads when a tile row is vector aligned and fully inside F (the 2-byte scalar form was LSU bound)
+  constexpr int V = Vec16<T>::N;
+  const bool vec_ok = (F % V == 0) && (f0 + RF_CHUNK <= F);
   // X tile: 32 rows x RF_CHUNK features
+  if (vec_ok) {
+    for (int i = tid; i < RF_MT * (RF_CHUNK / V); i += 256) {
+      const int r = i / (RF_CHUNK / V), q = i % (RF_CHUNK / V);
+      Vec16<T> v;
+      if (m0 + r < M) {
+        v.load(X + (size_t)(m0 + r) * F + f0 + q * V);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v.v[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) Xs[r][q * V + e] = v.v[e];
+    }
+  } else
   for (int i = tid; i < RF_MT * RF_CHUNK; i += 256) {
     const int r = i / RF_CHUNK, f = i % RF_CHUNK;
     float v = 0.f;
@@ -46,6 +63,20 @@ __global__ void __launch_bounds__(256) fc_reduce_f_kernel(const T* __restrict__ 
   const int mr = tid >> 3, nq = tid & 7;  // row mr, columns nq + 8*j
   for (int n0 = 0; n0 < N; n0 += RF_NT) {
     __syncthreads();
+    if (vec_ok) {
+      for (int i = tid; i < RF_NT * (RF_CHUNK / V); i += 256) {
+        const int r = i / (RF_CHUNK / V), q = i % (RF_CHUNK / V);
+        Vec16<T> v;
+        if (n0 + r < N) {
+          v.load(Wm + (size_t)(n0 + r) * F + f0 + q * V);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) v.v[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) Ws[r][q * V + e] = v.v[e];
+      }
+    } else
     for (int i = tid; i < RF_NT * RF_CHUNK; i += 256) {
       const int r = i / RF_CHUNK, f = i % RF_CHUNK;
       float v = 0.f;
@@ -118,6 +149,7 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
   const int tid = threadIdx.x;
   const bool patch = p.permC > 0 && p.permP % 16 == 0 && p.permC % 8 == 0;
   const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * WF_MT;
+  const bool bvec = !patch && (p.F % Vec16<TB>::N == 0) && (f0 + WF_FT <= p.F);   // 16-byte loads of the B tile
   int pc0 = 0, pp0 = 0;                       // patch origin (channel, pixel)
   if (patch) {
     const int ctiles = p.permC / 8;
@@ -148,9 +180,24 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
         const int cl = fl & 7, pl = fl >> 3;
         if (k0 + k < p.K) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + (size_t)(pp0 + pl) * p.permC + pc0 + cl]);
         Bs[k][cl * 16 + pl] = v;
-      } else {
+      } else if (!bvec) {
         if (k0 + k < p.K && f0 + fl < p.F) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + f0 + fl]);
         Bs[k][fl] = v;
+      }
+    }
+    if (!patch && bvec) {
+      constexpr int VB = Vec16<TB>::N;
+      for (int i = tid; i < WF_KT * (WF_FT / VB); i += 256) {
+        const int k = i / (WF_FT / VB), q = i % (WF_FT / VB);
+        Vec16<TB> v;
+        if (k0 + k < p.K) {
+          v.load(Bm + (size_t)(k0 + k) * p.F + f0 + q * VB);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VB; ++e) v.v[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < VB; ++e) Bs[k][q * VB + e] = v.v[e];
       }
     }
     __syncthreads();

@@ -492,11 +492,14 @@ static int gc_pick_cs(int B, int P, int C, int vec, size_t elem, int nslices, si
   if (const char* e = getenv("BVAE_GC_MAXCS")) max_cs = atoi(e);
   while (cs <= max_cs && !fits(cs, &smem)) cs <<= 1;
   if (cs > max_cs) return 0;
-  // widen while most SMs would idle and slices stay >= 16 KB
+  // widen while most SMs would idle and the slices stay large: every doubling adds cluster-barrier latency to five
+  // all-gathers, measured best down to 16 KB slices (the SE mat-vecs and per-channel reductions also split across the cluster)
   const int sms = num_sms();
+  size_t min_slice = 16384;
+  if (const char* e = getenv("BVAE_GC_MIN_SLICE")) min_slice = (size_t)atol(e);
   while ((long)B * cs < (sms * 3) / 4 && cs < 8) {
     size_t s2 = 0;
-    if (!fits(cs * 2, &s2) || (size_t)(P / (cs * 2)) * C * elem < 16384) break;
+    if (!fits(cs * 2, &s2) || (size_t)(P / (cs * 2)) * C * elem < min_slice) break;
     cs *= 2;
     smem = s2;
   }
