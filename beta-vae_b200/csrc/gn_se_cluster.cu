@@ -497,7 +497,7 @@ static int gc_pick_cs(int B, int P, int C, int vec, size_t elem, int nslices, si
   const int sms = num_sms();
   size_t min_slice = 16384;
   if (const char* e = getenv("BVAE_GC_MIN_SLICE")) min_slice = (size_t)atol(e);
-  while ((long)B * cs < (sms * 3) / 4 && cs < 8) {
+  while ((long)B * cs < (sms * 3) / 4 && cs < 8) {   // (8-CTA clusters at two CTAs per SM measured 2x slower)
     size_t s2 = 0;
     if (!fits(cs * 2, &s2) || (size_t)(P / (cs * 2)) * C * elem < min_slice) break;
     cs *= 2;
