@@ -149,7 +149,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self.nv is not None:
@@ -283,31 +283,23 @@ def cuda_main(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
 
-    # ---- (3) per-op CUDA-event pass for the roofline of the dominant kernel
+    # ---- (3) rooflines.  (a) eager per-op CUDA-event pass: ranks the C-ABI calls (host launch gaps inflate the small
+    #      ones, so it is only used for the `top_ops` table).  (b) the dominant kernel -- the stride-1 halo conv at
+    #      the heaviest layer shape (dec3: 128x128, 64 -> 64 channels; with its dgrad twin 9 % of the step) -- and the
+    #      two HBM-bound kernels north_star names are timed on the device: R launches captured in one CUDA graph,
+    #      inputs rotating through buffers that together exceed the 126 MB L2, CUDA events around the replay.
     prof = profiler.start()
     for i in range(args.steps):
         train_step_eager(xs[i % n_batches])
     agg = profiler.stop().summary()
     peaks = measured_peaks()
-    roofline, top = None, []
+    top = []
     if agg:
         total_ms = sum(a["ms"] for a in agg.values())
         ranked = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
-        tag, a = ranked[0]
-        per_call_ms = a["ms"] / a["calls"]
-        if tag.startswith("conv_") or tag.startswith("heads") or tag.startswith("fc_dec"):
-            ach = a["flops"] / a["calls"] / (per_call_ms * 1e-3) / 1e12
-            roofline = {"kernel": tag, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                        "peak_source": peaks["source"] + " (sustained bf16)"}
-        else:
-            ach = a["bytes"] / a["calls"] / (per_call_ms * 1e-3) / 1e9
-            roofline = {"kernel": tag, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
-        roofline.update({"ms_per_call": per_call_ms, "launches_per_call": a["launches"] / a["calls"],
-                         "share_of_profiled_step": a["ms"] / total_ms})
         if rank == 0:
-            print(f"# per-op CUDA-event profile: {total_ms / args.steps:.3f} ms/step inside C-ABI calls", file=sys.stderr)
+            print(f"# per-op CUDA-event profile (eager, includes launch gaps): {total_ms / args.steps:.3f} ms/step inside "
+                  f"C-ABI calls", file=sys.stderr)
             for t, v in ranked:
                 print(f"#  {t:42s} {v['ms'] / args.steps:8.4f} ms/step  {100 * v['ms'] / total_ms:5.1f}%  "
                       f"launches/call {v['launches'] / v['calls']:.0f}  "
@@ -317,6 +309,83 @@ def cuda_main(args):
             top.append({"op": t, "ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_ms,
                         "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else None,
                         "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else None})
+
+    from bvae_rt import ops
+    from bvae_rt.lib import BF16
+
+    def device_us(fn, reps):
+        """Average device time of one `fn(i)` launch group: `reps` of them captured in a CUDA graph, replayed 3x."""
+        fn(0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                fn(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(3):
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+        return best
+
+    step_us = ms / args.steps * 1e3
+    bf = torch.bfloat16
+    # (b1) dominant kernel: conv_halo_tc_kernel<64, resident> on dec3 (fprop; the dgrad launch is the same kernel)
+    Hc, Cc = size, cfg["model"]["base_channels"]
+    xs_c = [torch.randn(batch, Hc, Hc, Cc, device=dev).to(bf) for _ in range(3)]
+    w_c = torch.randn(Cc, Cc, 3, 3, device=dev) * 0.05
+    wp_c = ops.pack_conv(w_c, BF16, False, ops.conv_weight_layout(Hc, Hc, Cc, Cc, 1, BF16, 0))
+    b_c = torch.zeros(Cc, device=dev)
+    conv_us = device_us(lambda i: ops.conv3x3_fprop(xs_c[i % 3], wp_c, b_c, Cc, 1, BF16), 9)
+    conv_flops = 2.0 * batch * Hc * Hc * Cc * 9 * Cc
+    ach = conv_flops / conv_us / 1e6
+    roofline = {
+        "kernel": f"conv_halo_tc_kernel<64,resident> dec3 conv3x3 {Hc}x{Hc}x{Cc}->{Cc} (tcgen05 implicit GEMM, fprop = dgrad kernel)",
+        "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": ach / peaks["bf16_tflops_sustained"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of this launch at batch 32, profiles/r1_ncu_conv_halo.txt
+        "traffic": 83.39e6 if batch == 32 else None,
+        "algorithmic_bytes": 2.0 * batch * Hc * Hc * Cc * 2,
+        "peak_source": peaks["source"] + " (sustained bf16, cuBLAS)", "us_per_launch": conv_us,
+        "launches_per_step": 2, "share_of_step": 2 * conv_us / step_us,
+        "note": "SS-mode tcgen05 fetches operands at ~64 B/clk: ceiling N/(N+128) = 33 % of the tensor pipe at N = 64 "
+                "(ncu sm__pipe_tensor_cycles_active 33.4 %), see DESIGN.md 4.1",
+    }
+    del xs_c
+    # (b2) HBM-bound kernels named by north_star: GroupNorm+ReLU+SE (cluster kernel, dec2 shape; multi-pass, dec3 shape)
+    #      and the loss kernel (final conv + sigmoid + reconstruction loss)
+    more = []
+
+    def gn_case(Hs, C, nbuf):
+        R = max(1, C // cfg["model"]["se_reduction_ratio"])
+        ys = [torch.randn(batch, Hs, Hs, C, device=dev).to(bf) for _ in range(nbuf)]
+        gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        w1, b1 = torch.randn(R, C, device=dev) * 0.1, torch.zeros(R, device=dev)
+        w2, b2 = torch.randn(C, R, device=dev) * 0.1, torch.zeros(C, device=dev)
+        us = device_us(lambda i: ops.gn_relu_se_fwd(ys[i % nbuf], gam, bet, w1, b1, w2, b2), 2 * nbuf)
+        nbytes = 2.0 * ys[0].numel() * 2
+        more.append({"kernel": f"gn_relu_se_fwd {Hs}x{Hs}x{C}", "bound": "hbm", "achieved": nbytes / us / 1e3,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / us / 1e3 / peaks["hbm_gbs"],
+                     "traffic": None, "us_per_launch": us})
+
+    gn_case(size // 2, Cc, 8)
+    gn_case(size, Cc, 3)
+    hs_f = [torch.randn(batch, size, size, Cc, device=dev).to(bf) for _ in range(3)]
+    w_f = torch.randn(1, Cc, 3, 3, device=dev) * 0.05
+    b_f = torch.zeros(1, device=dev)
+    tgt = torch.rand(batch, 1, size, size, device=dev)
+    us = device_us(lambda i: ops.FinalConvSigmoidRecon.apply(hs_f[i % 3], w_f, b_f, tgt, 0), 6)
+    nbytes = hs_f[0].numel() * 2 + 8.0 * tgt.numel()
+    more.append({"kernel": "finalconv_sigmoid_recon_fwd (tcgen05 N=16 + fused sigmoid/loss epilogue)", "bound": "hbm",
+                 "achieved": nbytes / us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": nbytes / us / 1e3 / peaks["hbm_gbs"], "traffic": 70.57e6 if batch == 32 else None,
+                 "us_per_launch": us})
+    del hs_f
 
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -335,7 +404,7 @@ def cuda_main(args):
             "config": {"workload": "configs/beta_vae_se.yaml default Beta-VAE-SE train step "
                                    "(loss fwd + bwd + grad all-reduce + clip + Adam)",
                        "image_size": size, "per_gpu_batch": batch, "global_batch": batch * world,
-                       "objective": "capacity C=30 gamma=1, FFL 0.5 (torch.fft), mse",
+                       "objective": "capacity C=30 gamma=1, FFL 0.5 (cuFFT rfft2 + fused kernels), mse",
                        "parallelism": f"dp{world}",
                        "launch": "eager" if graphed is None else "whole step captured in one CUDA graph",
                        "l2": f"no explicit flush: a step streams ~{act_mb:.0f} MB of activations plus 8 rotating "
@@ -345,6 +414,7 @@ def cuda_main(args):
                     "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": 16},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_more": more,
             "cpu_baseline": cpu,
             "top_ops": top,
         }
@@ -363,7 +433,7 @@ def cuda_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: training.batch_size of the config)")
