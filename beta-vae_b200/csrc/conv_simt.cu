@@ -206,15 +206,15 @@ __global__ void __launch_bounds__(256)
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[9 * CIN * Cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int cv = Cout / V;
-  const long long total = (long long)B * Ho * Wo * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv);
-    long long r = i / cv;
-    const int ow = (int)(r % Wo);
-    r /= Wo;
-    const int oh = (int)(r % Ho);
-    const int b = (int)(r / Ho);
+  // 32-bit index arithmetic (host checks B*Ho*Wo*cv < 2^31): 64-bit div/mod per output dominated this loop
+  const unsigned total = (unsigned)B * Ho * Wo * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)cv);
+    unsigned r = i / (unsigned)cv;
+    const int ow = (int)(r % (unsigned)Wo);
+    r /= (unsigned)Wo;
+    const int oh = (int)(r % (unsigned)Ho);
+    const int b = (int)(r / (unsigned)Ho);
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = wsm[9 * CIN * Cout + c * V + k];
@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(256)
   for (long long m = p0 + row; m < p1; m += rows) {
     Vec16<TD> d;
     d.load(dy + (size_t)m * Cout + (size_t)col * V);
-    const int ow = (int)(m % Wo), oh = (int)((m / Wo) % Ho), b = (int)(m / ((long long)Wo * Ho));
+    const unsigned mu = (unsigned)m, rw = mu / (unsigned)Wo;   // 32-bit div/mod (host checks Mpix < 2^31)
+    const int ow = (int)(mu - rw * (unsigned)Wo), oh = (int)(rw % (unsigned)Ho), b = (int)(rw / (unsigned)Ho);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int ih = oh * stride + t / 3 - 1, iw = ow * stride + t % 3 - 1;
@@ -579,6 +580,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, float* dbias, 
     double* bpart = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) +
                                               align_up((size_t)pl.splits * Cin * 9 * Cout * sizeof(double), 256));
     const int cv = Cout / V, rows = 256 / cv > 0 ? 256 / cv : 1;
+    BVAE_REQUIRE((long long)B * Ho * Wo < (1LL << 31), BVAE_ERR_UNSUPPORTED, "conv3x3_wgrad(small Cin): too many pixels");
     dim3 grid(pl.splits, Cin);
     conv_smallcin_wgrad_kernel<TX, TD><<<grid, cv * rows, (size_t)rows * Cout * sizeof(float), st>>>(
         (const TX*)x, (const TD*)dy, dpart, dbias ? bpart : nullptr, B, H, W, Cin, Ho, Wo, Cout, stride, cv, rows,
@@ -629,6 +631,7 @@ extern "C" int bvae_conv3x3_fprop(const void* x, const void* wp, const float* bi
     const int V = (y_dtype == BVAE_BF16) ? 8 : 4;
     BVAE_REQUIRE(Cout % V == 0, BVAE_ERR_UNSUPPORTED, "conv3x3_fprop(small Cin): Cout=%d %% %d", Cout, V);
     const long long total = (long long)B * Ho * Wo * (Cout / V);
+    BVAE_REQUIRE(total < (1LL << 31) - (1LL << 24), BVAE_ERR_UNSUPPORTED, "conv3x3_fprop(small Cin): too many outputs");
     long long blocks = (total + 255) / 256;
     if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
 #define BVAE_SMALLCIN(TI, TO, CIN)                                                                              \
