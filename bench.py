@@ -32,6 +32,8 @@ import yaml  # noqa: E402
 CONFIG = os.path.join(PKG, "configs", "beta_vae_se.yaml")
 METRIC = "train images/sec (fwd+bwd)"
 LOSS_KW = dict(beta=1.0, capacity=30.0, free_bits=0.0, capacity_weight=1.0)
+WORKLOAD = "configs/beta_vae_se.yaml default Beta-VAE-SE train step (loss fwd + bwd + grad all-reduce + clip + Adam)"
+OBJECTIVE = "capacity C=30 gamma=1, FFL 0.5, mse"
 
 
 def weight_init(m):
@@ -102,8 +104,9 @@ def reference_main(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs/beta_vae_se.yaml default Beta-VAE-SE training step "
-                               "(loss+backward+clip+Adam), CPU fp32, batch 32", "batch_per_step": batch},
+        "config": {"workload": WORKLOAD, "image_size": cfg["data"]["image_size"], "per_gpu_batch": batch,
+                   "global_batch": batch, "objective": OBJECTIVE,
+                   "parallelism": "cpu: the reference path (oracle port) on all host cores, fp32"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} full train steps at batch {batch} (oracle port of the reference "
                                    f"path, torch CPU fp32, {threads} threads)"},
@@ -401,10 +404,9 @@ def cuda_main(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs/beta_vae_se.yaml default Beta-VAE-SE train step "
-                                   "(loss fwd + bwd + grad all-reduce + clip + Adam)",
+            "config": {"workload": WORKLOAD,
                        "image_size": size, "per_gpu_batch": batch, "global_batch": batch * world,
-                       "objective": "capacity C=30 gamma=1, FFL 0.5 (cuFFT rfft2 + fused kernels), mse",
+                       "objective": OBJECTIVE,
                        "parallelism": f"dp{world}",
                        "launch": "eager" if graphed is None else "whole step captured in one CUDA graph",
                        "l2": f"no explicit flush: a step streams ~{act_mb:.0f} MB of activations plus 8 rotating "
