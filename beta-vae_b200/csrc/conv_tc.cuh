@@ -51,6 +51,12 @@ bool conv_halo_final_supported(int H, int W, int C, int Co);
 int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, const float* target, float* recon,
                         double* lpart, int* n_lpart, int loss_type, int B, int H, int W, int C, int Co, cudaStream_t st);
 
+// ---- final conv backward on tcgen05 (finalconv_tc.cu): C = 64 -> 1 channel ----
+bool finalconv_bwd_tc_supported(int H, int W, int C, int Co);
+size_t finalconv_bwd_tc_dcol_bytes(int B, int H, int W);
+int finalconv_bwd_tc(const void* h, const float* w, const float* dlogit, void* dh, float* wpart, float* bpart, void* dcol_ws,
+                     int* ncta, int B, int H, int W, cudaStream_t st);
+
 // ---- wgrad (conv_tc_wgrad.cu) ----
 struct WgradTcPlan {
   int bn, slots, groups;           // co tile, accumulator slots per CTA, row-block groups

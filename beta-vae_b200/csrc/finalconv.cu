@@ -265,6 +265,7 @@ struct FinalWs {
   float* wpart;   // [kFcMaxCtas][Co][9][C]
   float* bpart;   // [kFcMaxCtas][Co]
   __nv_bfloat16* wp16;  // [9][16][C] bf16 weights for the tcgen05 forward (rows >= Co are zero)
+  void* dcol;           // tcgen05 backward: bf16 im2col of dlogit [B][H][W][16] + packed weights
   size_t bytes;
 };
 static FinalWs final_ws_carve(void* base, int B, int H, int W, int C, int Co) {
@@ -281,6 +282,7 @@ static FinalWs final_ws_carve(void* base, int B, int H, int W, int C, int Co) {
   w.wpart = reinterpret_cast<float*>(take((size_t)kFcMaxCtas * Co * 9 * C * sizeof(float)));
   w.bpart = reinterpret_cast<float*>(take((size_t)kFcMaxCtas * Co * sizeof(float)));
   w.wp16 = reinterpret_cast<__nv_bfloat16*>(take((size_t)9 * 16 * C * sizeof(__nv_bfloat16)));
+  w.dcol = take(finalconv_bwd_tc_supported(H, W, C, Co) ? finalconv_bwd_tc_dcol_bytes(B, H, W) : 0);
   w.bytes = off;
   return w;
 }
@@ -349,6 +351,15 @@ static int final_bwd_impl(const void* h, const float* w, const float* recon, con
   if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
   dlogit_kernel<<<(int)blocks, 256, 0, st>>>(recon, target, g_recon, g_loss, fw.dlogit, loss_type, 1.f / (float)B, n);
   BVAE_LAUNCH_CHECK("dlogit");
+  if (sizeof(T) == 2 && !final_tc_env_off() && finalconv_bwd_tc_supported(H, W, C, Co)) {
+    // tcgen05 path: both contractions (dh, dW) run against the 16-column im2col of dlogit
+    int ncta = 0;
+    const int rc = finalconv_bwd_tc(h, w, fw.dlogit, dh, fw.wpart, fw.bpart, fw.dcol, &ncta, B, H, W, st);
+    if (rc != BVAE_OK) return rc;
+    finalconv_wreduce_kernel<<<cdiv(Co * 9 * C + Co, 32), 256, 0, st>>>(fw.wpart, fw.bpart, dw, db, ncta, C, Co);
+    BVAE_LAUNCH_CHECK("finalconv_wreduce");
+    return BVAE_OK;
+  }
   const size_t sm = ((size_t)Co * 9 * C + (size_t)g.rows * C) * sizeof(float);
   BVAE_REQUIRE(sm <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "finalconv: C=%d too large", C);
   BVAE_REQUIRE((long long)B * H * W < (1LL << 31) - 65536 * 1024LL, BVAE_ERR_UNSUPPORTED, "finalconv_bwd: too many pixels");
