@@ -217,6 +217,37 @@ def conv3x3_wgrad(x, dy, stride, want_bias=True, dw=None, db=None):
     return dw, db
 
 
+def conv_first_supported(H, W, Cin, Cout, stride, dt):
+    return dt == BF16 and query("bvae_conv_first_supported", H, W, Cin, Cout, stride) == 1
+
+
+def conv_first_fprop(x, w, bias):
+    """First encoder layer on tcgen05: x [B,H,W,1] fp32 -> (y [B,H/2,W/2,64] bf16, xcol) where xcol is the 16-column
+    bf16 im2col (9 taps + ones column) that the weight gradient reuses."""
+    B, H, W, _ = x.shape
+    Ho, Wo = H // 2, W // 2
+    xcol = torch.empty((B, Ho, Wo, 16), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, Ho, Wo, 64), dtype=torch.bfloat16, device=x.device)
+    ws = _ws(query("bvae_conv_first_workspace"), x.device)
+    with profiler.region(f"conv_fprop[{H}x{W}x1->64,s2]", flops=2.0 * y.numel() * 9, nbytes=x.numel() * 4 + y.numel() * 2):
+        call("bvae_conv_first_im2col", _p(x), _p(xcol), B, H, W, _stream())
+        call("bvae_conv_first_fprop", _p(xcol), _p(w), _p(bias), _p(y), _p(ws), ws.numel(), B, Ho, Wo, _stream())
+    return y, xcol
+
+
+def conv_first_wgrad(xcol, dy, dw=None, db=None):
+    B, Ho, Wo, _ = xcol.shape
+    if dw is None:
+        dw = torch.empty((64, 1, 3, 3), dtype=torch.float32, device=dy.device)
+    if db is None:
+        db = torch.empty((64,), dtype=torch.float32, device=dy.device)
+    ws = _ws(query("bvae_conv_first_workspace"), dy.device)
+    with profiler.region(f"conv_wgrad[{2 * Ho}x{2 * Wo}x1->64,s2]", flops=2.0 * dy.numel() * 9,
+                         nbytes=xcol.numel() * 2 + dy.numel() * 2):
+        call("bvae_conv_first_wgrad", _p(xcol), _p(dy), _p(dw), _p(db), _p(ws), ws.numel(), B, Ho, Wo, _stream())
+    return dw, db
+
+
 def upsample2x_fwd(x):
     B, H, W, Cc = x.shape
     y = torch.empty((B, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
@@ -282,15 +313,24 @@ class ConvGnSeBlock(torch.autograd.Function):
         xin = upsample2x_fwd(x) if upsample else x
         _, H, W, Cin = xin.shape
         Cout = cw.shape[0]
-        lf = conv_weight_layout(H, W, Cin, Cout, stride, dt if code_of(xin) == dt else F32, 0)
-        lb = conv_weight_layout(H, W, Cin, Cout, stride, dt, 1)
-        wp = packs.get(f"{key}.fprop.{lf}", (cw,), dt, lambda: pack_conv(cw, dt, False, lf))
-        wpt = packs.get(f"{key}.dgrad.{lb}", (cw,), dt, lambda: pack_conv(cw, dt, True, lb))
-        y = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt)
+        first_tc = ((not upsample) and xin.dtype == torch.float32 and not x.requires_grad and
+                    conv_first_supported(H, W, Cin, Cout, stride, dt))
+        if first_tc:
+            # first encoder layer: 9-tap im2col of the image + one tcgen05 MMA per tile; xcol replaces x for the backward
+            y, xcol = conv_first_fprop(xin, cw, cb)
+            wpt = None
+            xin = xcol
+        else:
+            lf = conv_weight_layout(H, W, Cin, Cout, stride, dt if code_of(xin) == dt else F32, 0)
+            lb = conv_weight_layout(H, W, Cin, Cout, stride, dt, 1)
+            wp = packs.get(f"{key}.fprop.{lf}", (cw,), dt, lambda: pack_conv(cw, dt, False, lf))
+            wpt = packs.get(f"{key}.dgrad.{lb}", (cw,), dt, lambda: pack_conv(cw, dt, True, lb))
+            y = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt)
         out, saved = gn_relu_se_fwd(y, gw, gb, w1, b1, w2, b2)
         stats, cpos, spos, hidden, gate = saved
         ctx.save_for_backward(xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate, cw, cb)
-        ctx.stride, ctx.upsample = stride, upsample
+        ctx.stride, ctx.upsample, ctx.first_tc = stride, upsample, first_tc
+        ctx.in_shape = (x.shape[0], H, W, Cin)
         return out
 
     @staticmethod
@@ -299,6 +339,11 @@ class ConvGnSeBlock(torch.autograd.Function):
         dout = dout.contiguous()
         dy, dgw, dgb, dw1, db1, dw2, db2 = gn_relu_se_bwd(dout, y, gw, gb, w1, b1, w2, b2,
                                                           (stats, cpos, spos, hidden, gate))
+        if ctx.first_tc:
+            if ctx.needs_input_grad[0]:
+                raise lib.BvaeError("the tcgen05 first-layer path does not produce an input gradient")
+            dcw, dcb = conv_first_wgrad(xin, dy, dw=grad_out(cw), db=grad_out(cb))
+            return None, dcw, dcb, dgw, dgb, dw1, db1, dw2, db2, None, None, None, None, None
         dcw, dcb = conv3x3_wgrad(xin, dy, ctx.stride, dw=grad_out(cw), db=grad_out(cb))
         dx = None
         if ctx.needs_input_grad[0]:

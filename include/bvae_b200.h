@@ -87,6 +87,17 @@ int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, float* dbias, v
                        int B, int H, int W, int Cin, int Cout, int stride, int x_dtype, int dy_dtype,
                        bvae_stream_t stream);
 
+/* First encoder layer (Cin = 1, stride 2, Cout = 64; nn.Conv2d at beta_vae.py:37 with in_ch = 1) on tcgen05:
+ * xcol [B][H/2][W/2][16] bf16 is the 9-tap im2col of the fp32 image x [B][H][W] plus a ones column, built once per
+ * forward and reused by the weight gradient.  y / dy [B][H/2][W/2][64] bf16; dw [64][1][3][3], db [64] fp32. */
+int bvae_conv_first_supported(int H, int W, int Cin, int Cout, int stride);
+int bvae_conv_first_im2col(const float* x, void* xcol, int B, int H, int W, bvae_stream_t stream);
+size_t bvae_conv_first_workspace(void);
+int bvae_conv_first_fprop(const void* xcol, const float* w, const float* bias, void* y, void* ws, size_t ws_bytes, int B,
+                          int Ho, int Wo, bvae_stream_t stream);
+int bvae_conv_first_wgrad(const void* xcol, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B, int Ho,
+                          int Wo, bvae_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Bilinear x2 upsample, align_corners=False (nn.Upsample at beta_vae.py:53).
  *   x [B][H][W][C] -> y [B][2H][2W][C];  bwd: dy [B][2H][2W][C] -> dx [B][H][W][C].

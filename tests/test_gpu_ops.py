@@ -422,3 +422,28 @@ def test_focal_frequency_loss_core(shape, alpha):
     (got * 1.7).backward()
     assert rel_err(got, want) <= 2e-5
     assert rel_err(pd.grad / 1.7, pr.grad) <= 5e-5
+
+
+@pytest.mark.parametrize("B,size", [(2, 32), (3, 64), (5, 128)])
+def test_conv_first_layer_tcgen05(B, size):
+    """First encoder layer (1 -> 64 channels, stride 2) through the im2col + tcgen05 path against F.conv2d on the
+    bf16-rounded image / weights (what conv2d sees under autocast)."""
+    ops = _ops()
+    if not ops.conv_first_supported(size, size, 1, 64, 2, ops.BF16):
+        pytest.skip("shape not covered by the tcgen05 first-layer path")
+    g = torch.Generator().manual_seed(B + size)
+    x = torch.floor(torch.rand(B, 1, size, size, generator=g) * 255) / 255
+    w = torch.randn(64, 1, 3, 3, generator=g) / 3
+    b = torch.randn(64, generator=g) * 0.1
+    xr = rnd(x, torch.bfloat16)
+    wr = rnd(w, torch.bfloat16).requires_grad_(True)
+    br = rnd(b, torch.bfloat16).requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=2, padding=1)
+    dy = rnd(torch.randn(yr.shape, generator=g), torch.bfloat16)
+    yr.backward(dy)
+    xd = x.to(dev()).view(B, size, size, 1).contiguous()
+    y, xcol = ops.conv_first_fprop(xd, w.to(dev()), b.to(dev()))
+    assert rel_err(nchw(y), yr) <= 1e-2
+    dw, db = ops.conv_first_wgrad(xcol, nhwc(dy, torch.bfloat16))
+    assert rel_err(dw, wr.grad) <= 5e-4          # fp32 accumulation of bf16 products
+    assert rel_err(db, br.grad) <= 5e-4
