@@ -113,10 +113,12 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
   const int p0 = chunk * pc, p1 = min(P, p0 + pc);
-  float g[V], bt[V], cnt[V], sx[V];
+  // z = (y - mean) * (rstd * gamma) + beta is the pre-activation in every pass of both kernel families (see
+  // gn_se_cluster.cu): the relu mask z > 0 is identical everywhere
+  float za[V], bt[V], cnt[V], sx[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    g[i] = gamma[col * V + i];
+    za[i] = rstd * gamma[col * V + i];
     bt[i] = beta[col * V + i];
     cnt[i] = 0.f;
     sx[i] = 0.f;
@@ -128,12 +130,14 @@ __global__ void __launch_bounds__(kGnThreads)
     v.load(base + (size_t)p * C);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float xh = (v.v[i] - mean) * rstd;
-      const bool pos = fmaf(xh, g[i], bt[i]) > 0.f;
+      const float vm = v.v[i] - mean;
+      const bool pos = fmaf(vm, za[i], bt[i]) > 0.f;
       cnt[i] += pos ? 1.f : 0.f;
-      sx[i] += pos ? xh : 0.f;
+      sx[i] += pos ? vm : 0.f;
     }
   }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sx[i] *= rstd;
   float* s0 = sm;
   float* s1 = sm + rows * C;
   if (row < rows) {
@@ -252,12 +256,12 @@ __global__ void __launch_bounds__(kGnThreads)
   }
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
   const int p0 = chunk * pc, p1 = min(P, p0 + pc);
-  float g[V], bt[V], sc[V];
+  float zs[V], bs_[V];   // gate folded in: relu(z) * s = max(z * s, 0) for the sigmoid gate s > 0
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    g[i] = gamma[col * V + i];
-    bt[i] = beta[col * V + i];
-    sc[i] = gate ? gate[(size_t)b * C + col * V + i] : 1.f;
+    const float sc = gate ? gate[(size_t)b * C + col * V + i] : 1.f;
+    zs[i] = rstd * gamma[col * V + i] * sc;
+    bs_[i] = beta[col * V + i] * sc;
   }
   const size_t off = ((size_t)b * P) * C + (size_t)col * V;
 #pragma unroll 4
@@ -265,11 +269,7 @@ __global__ void __launch_bounds__(kGnThreads)
     Vec16<T> v;
     v.load(y + off + (size_t)p * C);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      // same expression as the pool/backward passes so the >0 mask is identical everywhere
-      const float xh = (v.v[i] - mean) * rstd;
-      v.v[i] = fmaxf(fmaf(xh, g[i], bt[i]), 0.f) * sc[i];
-    }
+    for (int i = 0; i < V; ++i) v.v[i] = fmaxf(fmaf(v.v[i] - mean, zs[i], bs_[i]), 0.f);
     v.store(out + off + (size_t)p * C);
   }
 }
@@ -287,10 +287,10 @@ __global__ void __launch_bounds__(kGnThreads)
   const float mean = stats[2 * b], rstd = stats[2 * b + 1];
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
   const int p0 = chunk * pc, p1 = min(P, p0 + pc);
-  float g[V], bt[V], a1[V], a2[V];
+  float za[V], bt[V], a1[V], a2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    g[i] = gamma[col * V + i];
+    za[i] = rstd * gamma[col * V + i];
     bt[i] = beta[col * V + i];
     a1[i] = 0.f;
     a2[i] = 0.f;
@@ -303,12 +303,14 @@ __global__ void __launch_bounds__(kGnThreads)
     d.load(dout + off + (size_t)p * C);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float xh = (v.v[i] - mean) * rstd;
-      const float dm = (fmaf(xh, g[i], bt[i]) > 0.f) ? d.v[i] : 0.f;
+      const float vm = v.v[i] - mean;
+      const float dm = (fmaf(vm, za[i], bt[i]) > 0.f) ? d.v[i] : 0.f;
       a1[i] += dm;
-      a2[i] = fmaf(dm, xh, a2[i]);
+      a2[i] = fmaf(dm, vm, a2[i]);
     }
   }
+#pragma unroll
+  for (int i = 0; i < V; ++i) a2[i] *= rstd;
   float* s0 = sm;
   float* s1 = sm + rows * C;
   if (row < rows) {
@@ -591,14 +593,18 @@ __global__ void __launch_bounds__(kGnThreads)
   const float S1 = coef[2 * b] * invM, S2 = coef[2 * b + 1] * invM;
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
   const int p0 = chunk * pc, p1 = min(P, p0 + pc);
-  float g[V], bt[V], sc[V], dp[V];
+  // dy = rstd * (gg*gamma - mean(gg*gamma) - xhat * mean(gg*gamma*xhat)),  gg = mask ? dout*gate + dpool : 0
+  //    = (mask ? dout * c1 + c2 : 0) + (y - mean) * k2 + k1
+  float za[V], bt[V], c1[V], c2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    g[i] = gamma[col * V + i];
+    const float rg = rstd * gamma[col * V + i];
+    za[i] = rg;
     bt[i] = beta[col * V + i];
-    sc[i] = gate ? gate[(size_t)b * C + col * V + i] : 1.f;
-    dp[i] = gate ? dpool[(size_t)b * C + col * V + i] : 0.f;
+    c1[i] = rg * (gate ? gate[(size_t)b * C + col * V + i] : 1.f);
+    c2[i] = rg * (gate ? dpool[(size_t)b * C + col * V + i] : 0.f);
   }
+  const float k1 = -rstd * S1, k2 = -rstd * rstd * S2;
   const size_t off = ((size_t)b * P) * C + (size_t)col * V;
 #pragma unroll 2
   for (int p = p0 + row; row < rows && p < p1; p += rows) {
@@ -607,10 +613,9 @@ __global__ void __launch_bounds__(kGnThreads)
     d.load(dout + off + (size_t)p * C);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float xh = (v.v[i] - mean) * rstd;
-      const float gg = (fmaf(xh, g[i], bt[i]) > 0.f) ? fmaf(d.v[i], sc[i], dp[i]) : 0.f;
-      // dy = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat))
-      d.v[i] = rstd * (fmaf(gg, g[i], -S1) - xh * S2);
+      const float vm = v.v[i] - mean;
+      const float t = (fmaf(vm, za[i], bt[i]) > 0.f) ? fmaf(d.v[i], c1[i], c2[i]) : 0.f;
+      d.v[i] = t + fmaf(vm, k2, k1);
     }
     d.store(dy + off + (size_t)p * C);
   }

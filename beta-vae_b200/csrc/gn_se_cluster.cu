@@ -64,6 +64,8 @@ __device__ __forceinline__ void gc_load_slice(void* dst, const void* src, uint32
 }
 
 // Per-channel sums over this CTA's pixels of two per-thread accumulator sets -> out0[c], out1[c] (double, fixed order).
+// G = min(8, threads / C) threads share a channel (adjacent lanes), each summing every G-th row in double, then a
+// fixed-order shuffle combine: the one-thread-per-channel loop over up to 64 rows was a serial latency chain.
 template <int V>
 __device__ __forceinline__ void gc_channel_reduce(const float (&a0)[V], const float (&a1)[V], float* scratch, int C, int cv,
                                                   int rows, float* out0, float* out1) {
@@ -76,14 +78,36 @@ __device__ __forceinline__ void gc_channel_reduce(const float (&a0)[V], const fl
     s1[row * C + col * V + i] = a1[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  int G = (int)blockDim.x / C;
+  G = G >= 8 ? 8 : (G >= 4 ? 4 : (G >= 2 ? 2 : 1));
+  if (G > rows) G = 1;
+  if (G > 1) {
+    const int c = threadIdx.x / G, g = threadIdx.x % G;
     double a = 0.0, q = 0.0;
-    for (int r = 0; r < rows; ++r) {
-      a += (double)s0[r * C + c];
-      q += (double)s1[r * C + c];
+    if (c < C) {
+      for (int r = g; r < rows; r += G) {
+        a += (double)s0[r * C + c];
+        q += (double)s1[r * C + c];
+      }
     }
-    out0[c] = (float)a;
-    out1[c] = (float)q;
+    for (int o = 1; o < G; o <<= 1) {     // all 32 lanes participate; groups are G-aligned within a warp
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (c < C && g == 0) {
+      out0[c] = (float)a;
+      out1[c] = (float)q;
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double a = 0.0, q = 0.0;
+      for (int r = 0; r < rows; ++r) {
+        a += (double)s0[r * C + c];
+        q += (double)s1[r * C + c];
+      }
+      out0[c] = (float)a;
+      out1[c] = (float)q;
+    }
   }
   __syncthreads();
 }
@@ -143,7 +167,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     gc_load_slice(ys, src, slice_bytes, bar);
   }
-  cluster.sync();          // every CTA of the cluster is running (and its barrier initialised) before any DSMEM access
+  __syncthreads();         // barrier initialised before anyone waits on it
   gc_mbar_wait(bar, 0);
 
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
@@ -160,6 +184,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   }
   const double ds = block_sum((double)s, red);
   const double dss = block_sum((double)ss, red);
+  cluster.sync();          // every CTA of the cluster is running before the first DSMEM access (hidden behind the load)
   if (threadIdx.x < CS) {  // all-gather: my partial into slot `rank` of every CTA
     double* dst = cluster.map_shared_rank(st_gather, threadIdx.x);
     dst[2 * rank] = ds;
@@ -177,10 +202,12 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   if (var < 0.0) var = 0.0;
   const float mean = (float)dmean, rstd = (float)(1.0 / sqrt(var + (double)kGcEps));
 
-  float g[V], bt[V], sc[V];
+  // z = (y - mean) * (rstd * gamma) + beta  is THE pre-activation in every pass (forward and backward, both kernel
+  // families): one FADD + one FFMA per element, and the relu mask z > 0 is identical everywhere.
+  float za[V], bt[V], sc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    g[i] = gamma[col * V + i];
+    za[i] = rstd * gamma[col * V + i];
     bt[i] = beta[col * V + i];
     sc[i] = 1.f;
   }
@@ -194,12 +221,14 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       v.load(ys + (size_t)p * C + col * V);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float xh = (v.v[i] - mean) * rstd;
-        const bool pos = fmaf(xh, g[i], bt[i]) > 0.f;
+        const float vm = v.v[i] - mean;
+        const bool pos = fmaf(vm, za[i], bt[i]) > 0.f;
         cnt[i] += pos ? 1.f : 0.f;
-        sx[i] += pos ? xh : 0.f;
+        sx[i] += pos ? vm : 0.f;           // sum of (y - mean); scaled by rstd once below
       }
     }
+#pragma unroll
+    for (int i = 0; i < V; ++i) sx[i] *= rstd;
     gc_channel_reduce<V>(cnt, sx, scratch, C, cv, rows, v_p0, v_p1);
     for (int r = 0; r < CS; ++r) {  // all-gather my [2][C] partials
       float* dst = cluster.map_shared_rank(gather, r) + (size_t)rank * 2 * C;
@@ -221,40 +250,54 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       v_pool[c] = (gamma[c] * qf + beta[c] * af) / (float)P;   // mean over pixels of relu(gn(y))
     }
     __syncthreads();
-    // ---- 3. excitation, split across the cluster: hidden[j] for j = rank, rank + CS, ...
+    // ---- 3. excitation.  Small SE blocks (C*R <= 4096 weights): every CTA computes all of it, no all-gather;
+    //         otherwise hidden[j] for j = rank, rank + CS, ... and gate[c] for this CTA's channel slice, all-gathered.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int j = rank + warp * CS; j < R; j += nwarp * CS) {
+    const bool split = CS > 1 && (long)C * R > 4096;
+    const int jstep = split ? CS : 1, j0 = split ? rank : 0;
+    for (int j = j0 + warp * jstep; j < R; j += nwarp * jstep) {
       float acc = 0.f;
       for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], v_pool[c], acc);
       acc = warp_sum(acc);
       const float h = fmaxf(acc + b1[j], 0.f);
-      if (lane < CS) cluster.map_shared_rank(v_hid, lane)[j] = h;
+      if (split) {
+        if (lane < CS) cluster.map_shared_rank(v_hid, lane)[j] = h;
+      } else if (lane == 0) {
+        v_hid[j] = h;
+      }
     }
-    cluster.sync();
-    // gate[c] for my channel slice, then all-gather
-    const int cpr = (C + CS - 1) / CS;
-    for (int c = rank * cpr + threadIdx.x; c < min(C, (rank + 1) * cpr); c += blockDim.x) {
+    if (split) cluster.sync(); else __syncthreads();
+    const int cpr = split ? (C + CS - 1) / CS : C;
+    const int c_lo = split ? rank * cpr : 0, c_hi = split ? min(C, (rank + 1) * cpr) : C;
+    for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
       float acc = b2[c];
       const float* wr = w2 + (size_t)c * R;
 #pragma unroll 8
       for (int j = 0; j < R; ++j) acc = fmaf(wr[j], v_hid[j], acc);
       const float gt = 1.0f / (1.0f + expf(-acc));
-      for (int r = 0; r < CS; ++r) cluster.map_shared_rank(v_gate, r)[c] = gt;
+      if (split) {
+        for (int r = 0; r < CS; ++r) cluster.map_shared_rank(v_gate, r)[c] = gt;
+      } else {
+        v_gate[c] = gt;
+      }
     }
-    cluster.sync();
+    if (split) cluster.sync(); else __syncthreads();
 #pragma unroll
     for (int i = 0; i < V; ++i) sc[i] = v_gate[col * V + i];
   }
   // ---- 4. normalise + relu + rescale, one write
   T* dst = out + ((size_t)b * P + (size_t)rank * pix) * C;
+  float zs[V], bs_[V];   // gate folded in: relu(z) * s = max(z * s, 0) for the sigmoid gate s > 0
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    zs[i] = za[i] * sc[i];
+    bs_[i] = bt[i] * sc[i];
+  }
   for (int p = row; p < pix; p += rows) {
     Vec16<T> v;
     v.load(ys + (size_t)p * C + col * V);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float xh = (v.v[i] - mean) * rstd;
-      v.v[i] = fmaxf(fmaf(xh, g[i], bt[i]), 0.f) * sc[i];
-    }
+    for (int i = 0; i < V; ++i) v.v[i] = fmaxf(fmaf(v.v[i] - mean, zs[i], bs_[i]), 0.f);
     v.store(dst + (size_t)p * C + col * V);
   }
   // ---- 5. saved tensors
@@ -325,15 +368,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   }
   const float mean = stats[2 * b], rstd = stats[2 * b + 1];
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
-  float g[V], bt[V];
+  float g[V], za[V], bt[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     g[i] = gamma[col * V + i];
+    za[i] = rstd * g[i];
     bt[i] = beta[col * V + i];
   }
   if (has_se)
     for (int c = threadIdx.x; c < C; c += blockDim.x) v_gate[c] = gate_g[(size_t)b * C + c];
-  cluster.sync();          // every CTA of the cluster is running before any DSMEM access
+  __syncthreads();         // barrier initialised, gate staged
   gc_mbar_wait(bar, 0);
 
   // ---- 1. A1[c] = sum dout*m, A2[c] = sum dout*m*xhat over this CTA's pixels
@@ -347,13 +391,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     d.load(dsrc + (size_t)p * C + col * V);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float xh = (v.v[i] - mean) * rstd;
-      const float dm = (fmaf(xh, g[i], bt[i]) > 0.f) ? d.v[i] : 0.f;
+      const float vm = v.v[i] - mean;
+      const float dm = (fmaf(vm, za[i], bt[i]) > 0.f) ? d.v[i] : 0.f;
       a1[i] += dm;
-      a2[i] = fmaf(dm, xh, a2[i]);
+      a2[i] = fmaf(dm, vm, a2[i]);          // sum of dm * (y - mean); scaled by rstd once below
     }
   }
+#pragma unroll
+  for (int i = 0; i < V; ++i) a2[i] *= rstd;
   gc_channel_reduce<V>(a1, a2, scratch, C, cv, rows, v_p0, v_p1);
+  cluster.sync();          // every CTA of the cluster is running before the first DSMEM access (hidden behind the pass above)
   for (int r = 0; r < CS; ++r) {
     float* dst = cluster.map_shared_rank(gather, r) + (size_t)rank * 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -381,11 +428,12 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   // ---- 2. SE backward, split across the cluster
   if (has_se) {
     // dz1[j] = (hidden > 0) * sum_c dz2[c] W2[c][j].  W2 is [C][R]: threads run along j (coalesced rows), channel
-    // groups in parallel; this CTA covers the channel slice [rank*cpr, (rank+1)*cpr) and the cluster all-gathers
-    // the partial sums.
+    // groups in parallel.  Large SE blocks split the channel range across the cluster and all-gather the partial sums;
+    // small ones (C*R <= 4096) are done whole by every CTA.
+    const bool split = CS > 1 && (long)C * R > 4096;
     {
-      const int cpr = (C + CS - 1) / CS;
-      const int c_lo = rank * cpr, c_hi = min(C, (rank + 1) * cpr);
+      const int cpr = split ? (C + CS - 1) / CS : C;
+      const int c_lo = split ? rank * cpr : 0, c_hi = split ? min(C, (rank + 1) * cpr) : C;
       const int ng = max(1, (int)blockDim.x / R);
       float part = 0.f;
       const int jj = threadIdx.x % R, cgp = threadIdx.x / R;
@@ -396,26 +444,39 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       if ((int)threadIdx.x < R) {
         double acc = 0.0;   // signed terms that cancel: combine the partials in double
         for (int q = 0; q < ng; ++q) acc += (double)scratch[q * R + threadIdx.x];
-        const float af = (float)acc;
-        for (int r = 0; r < CS; ++r) cluster.map_shared_rank(gather, r)[(size_t)CS * 2 * C + rank * R + threadIdx.x] = af;
+        if (split) {
+          const float af = (float)acc;
+          for (int r = 0; r < CS; ++r) cluster.map_shared_rank(gather, r)[(size_t)CS * 2 * C + rank * R + threadIdx.x] = af;
+        } else {
+          v_dz1[threadIdx.x] = hidden_g[(size_t)b * R + threadIdx.x] > 0.f ? (float)acc : 0.f;
+        }
       }
-      cluster.sync();
-      if ((int)threadIdx.x < R) {
-        double acc = 0.0;
-        for (int r = 0; r < CS; ++r) acc += (double)gather[(size_t)CS * 2 * C + r * R + threadIdx.x];
-        v_dz1[threadIdx.x] = hidden_g[(size_t)b * R + threadIdx.x] > 0.f ? (float)acc : 0.f;
+      if (split) {
+        cluster.sync();
+        if ((int)threadIdx.x < R) {
+          double acc = 0.0;
+          for (int r = 0; r < CS; ++r) acc += (double)gather[(size_t)CS * 2 * C + r * R + threadIdx.x];
+          v_dz1[threadIdx.x] = hidden_g[(size_t)b * R + threadIdx.x] > 0.f ? (float)acc : 0.f;
+        }
       }
       __syncthreads();
     }
-    const int cpr = (C + CS - 1) / CS;
-    for (int c = rank * cpr + threadIdx.x; c < min(C, (rank + 1) * cpr); c += blockDim.x) {
-      float dp = 0.f;
+    {
+      const int cpr = split ? (C + CS - 1) / CS : C;
+      const int c_lo = split ? rank * cpr : 0, c_hi = split ? min(C, (rank + 1) * cpr) : C;
+      for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+        float dp = 0.f;
 #pragma unroll 8
-      for (int j = 0; j < R; ++j) dp = fmaf(v_dz1[j], w1[(size_t)j * C + c], dp);
-      dp /= (float)P;
-      for (int r = 0; r < CS; ++r) cluster.map_shared_rank(v_dp, r)[c] = dp;
+        for (int j = 0; j < R; ++j) dp = fmaf(v_dz1[j], w1[(size_t)j * C + c], dp);
+        dp /= (float)P;
+        if (split) {
+          for (int r = 0; r < CS; ++r) cluster.map_shared_rank(v_dp, r)[c] = dp;
+        } else {
+          v_dp[c] = dp;
+        }
+      }
+      if (split) cluster.sync(); else __syncthreads();
     }
-    cluster.sync();
   }
   // ---- 3. G1, G2 per channel, S1, S2 per sample (every CTA computes the same values in the same order)
   double s1 = 0.0, s2 = 0.0;
@@ -444,12 +505,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   const float invM = 1.0f / ((float)P * (float)C);
   const float S1 = (float)s1 * invM, S2 = (float)s2 * invM;
   // ---- 4. dy
-  float sc[V], dpv[V];
+  // dy = rstd * (gg * gamma - S1 - xhat * S2),  gg = mask ? dout * gate + dpool : 0
+  //    = (mask ? dout * c1 + c2 : 0) + (y - mean) * k2 + k1      with the per-channel / per-sample constants below
+  float c1[V], c2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    sc[i] = has_se ? v_gate[col * V + i] : 1.f;
-    dpv[i] = has_se ? v_dp[col * V + i] : 0.f;
+    const float rg = rstd * g[i];
+    c1[i] = rg * (has_se ? v_gate[col * V + i] : 1.f);
+    c2[i] = rg * (has_se ? v_dp[col * V + i] : 0.f);
   }
+  const float k1 = -rstd * S1, k2 = -rstd * rstd * S2;
   T* dstp = dy + goff;
   for (int p = row; p < pix; p += rows) {
     Vec16<T> v, d;
@@ -457,9 +522,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     d.load(dsrc + (size_t)p * C + col * V);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float xh = (v.v[i] - mean) * rstd;
-      const float gg = (fmaf(xh, g[i], bt[i]) > 0.f) ? fmaf(d.v[i], sc[i], dpv[i]) : 0.f;
-      d.v[i] = rstd * (fmaf(gg, g[i], -S1) - xh * S2);
+      const float vm = v.v[i] - mean;
+      const float t = (fmaf(vm, za[i], bt[i]) > 0.f) ? fmaf(d.v[i], c1[i], c2[i]) : 0.f;
+      d.v[i] = t + fmaf(vm, k2, k1);
     }
     d.store(dstp + (size_t)p * C + col * V);
   }
