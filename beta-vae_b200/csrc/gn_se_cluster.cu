@@ -272,8 +272,22 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
       float acc = b2[c];
       const float* wr = w2 + (size_t)c * R;
-#pragma unroll 8
-      for (int j = 0; j < R; ++j) acc = fmaf(wr[j], v_hid[j], acc);
+      if ((R & 3) == 0) {   // 16-byte loads of the thread's own W2 row, four independent chains
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float4* wq = reinterpret_cast<const float4*>(wr);
+        const float4* hq = reinterpret_cast<const float4*>(v_hid);
+#pragma unroll 4
+        for (int j = 0; j < R / 4; ++j) {
+          const float4 w4 = wq[j], h4 = hq[j];
+          a4[0] = fmaf(w4.x, h4.x, a4[0]);
+          a4[1] = fmaf(w4.y, h4.y, a4[1]);
+          a4[2] = fmaf(w4.z, h4.z, a4[2]);
+          a4[3] = fmaf(w4.w, h4.w, a4[3]);
+        }
+        acc += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+      } else {
+        for (int j = 0; j < R; ++j) acc = fmaf(wr[j], v_hid[j], acc);
+      }
       const float gt = 1.0f / (1.0f + expf(-acc));
       if (split) {
         for (int r = 0; r < CS; ++r) cluster.map_shared_rank(v_gate, r)[c] = gt;
