@@ -352,7 +352,7 @@ def cuda_main(args):
         "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": ach / peaks["bf16_tflops_sustained"],
         # dram__bytes_read.sum + dram__bytes_write.sum of this launch at batch 32, profiles/r1_ncu_conv_halo.txt
-        "traffic": 83.39e6 if batch == 32 else None,
+        "traffic": 84.93e6 if batch == 32 else None,
         "algorithmic_bytes": 2.0 * batch * Hc * Hc * Cc * 2,
         "peak_source": peaks["source"] + " (sustained bf16, cuBLAS)", "us_per_launch": conv_us,
         "launches_per_step": 2, "share_of_step": 2 * conv_us / step_us,

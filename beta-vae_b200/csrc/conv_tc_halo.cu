@@ -437,7 +437,6 @@ int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, cons
   const size_t wbytes = (size_t)9 * C * 16 * 2;
   int sa = (int)((HL_SMEM_MAX - 1024 - bar_bytes - wbytes) / HL_HALO_SLOT);
   p.sa = sa > 8 ? 8 : sa;
-  if (const char* e = getenv("BVAE_HALO_SA")) p.sa = atoi(e);  // dev knob
   p.b_off = 0;
   p.a_off = (uint32_t)align_up(wbytes, 1024);
   p.bar_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;

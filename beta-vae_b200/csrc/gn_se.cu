@@ -1,4 +1,7 @@
-// GroupNorm(1,C) + ReLU + Squeeze-and-Excitation, fused forward / backward (memory bound).
+// GroupNorm(1,C) + ReLU + Squeeze-and-Excitation, fused forward / backward (memory bound): the multi-pass
+// kernels and the C-ABI entry points.  Samples that fit a thread-block cluster's shared memory (<= 1 MB) take the
+// single-launch cluster-resident kernels of gn_se_cluster.cu instead; these kernels serve larger samples (dec3 of the
+// default config), channel counts the cluster mapping does not cover, and BVAE_GN_NO_CLUSTER=1.
 //
 // Replaces native_group_norm + relu_ + adaptive_avg_pool2d + 2x linear + sigmoid + mul
 // (reference: src/models/beta_vae.py:41-46, 61-66; src/models/se_blocks.py:15-19) and their
