@@ -250,6 +250,14 @@ class TrainEngine:
         ops.set_grad_arena(None)
 
 
+class StagedBatch:
+    """A batch whose host->device copy is in flight on the copy stream (``GraphedTrainStep.prefetch``)."""
+    __slots__ = ("slot", "buf", "ready")
+
+    def __init__(self, slot, buf, ready):
+        self.slot, self.buf, self.ready = slot, buf, ready
+
+
 class GraphedTrainStep:
     """One whole training step -- zero_grad, ``BetaVAE.loss`` under autocast, backward, bucketed
     gradient all-reduce, clip + Adam -- captured once into a CUDA graph and replayed.
@@ -264,7 +272,12 @@ class GraphedTrainStep:
     The first ``eager_steps`` calls run un-captured (they are real steps and warm up lazy
     initialisation: cuFFT plans, smem attributes); the next call captures, and every call from
     then on replays.  Returns ``model.loss``'s dictionary; its tensors are the graph's static
-    outputs and are overwritten by the next call."""
+    outputs and are overwritten by the next call.
+
+    ``prefetch(x_host)`` starts the next batch's host->device copy on a separate stream (two staging
+    buffers), so the PCIe transfer overlaps the current step's kernels the way the reference's
+    ``DataLoader(pin_memory=True)`` + ``non_blocking`` copy overlaps its Python-bound step; pass the
+    returned ``StagedBatch`` to ``__call__``."""
 
     def __init__(self, engine: "TrainEngine", batch_shape, autocast_dtype=torch.bfloat16, eager_steps: int = 2,
                  seed: int = 0):
@@ -280,6 +293,37 @@ class GraphedTrainStep:
         self._kw = None
         self.launches_per_step = None
         self._gen = torch.Generator(device=dev).manual_seed(seed)
+        self._copy_stream = None
+        self._stage = None
+        self._consumed = [None, None]
+        self._slot = 0
+
+    def prefetch(self, x) -> "StagedBatch":
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+            self._stage = [torch.empty_like(self.x) for _ in range(2)]
+        slot = self._slot
+        self._slot ^= 1
+        buf = self._stage[slot]
+        cs = self._copy_stream
+        if self._consumed[slot] is not None:
+            cs.wait_event(self._consumed[slot])      # the step that read this buffer two batches ago
+        with torch.cuda.stream(cs):
+            buf.copy_(x, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        return StagedBatch(slot, buf, ready)
+
+    def _load_input(self, x):
+        if isinstance(x, StagedBatch):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(x.ready)
+            self.x.copy_(x.buf, non_blocking=True)   # device-to-device into the graph's static input
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._consumed[x.slot] = done
+        else:
+            self.x.copy_(x, non_blocking=True)
 
     def _body(self, kw):
         self.engine.zero_grad()
@@ -306,7 +350,7 @@ class GraphedTrainStep:
         self.graph, self.out, self._kw = g, out, dict(kw)
 
     def __call__(self, x, eps=None, **kw):
-        self.x.copy_(x, non_blocking=True)
+        self._load_input(x)
         if eps is None:
             self.eps.normal_(generator=self._gen)
         else:

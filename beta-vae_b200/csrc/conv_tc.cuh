@@ -48,7 +48,8 @@ int conv_halo_launch(const void* src, const void* wp_nk, const float* bias, void
                      int dgrad, cudaStream_t st);
 
 bool conv_halo_final_supported(int H, int W, int C, int Co);
-int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, const float* target, float* recon,
+int conv_halo_final_rows(int Co);   // rows of the [rows][C] weight pack (9 * Co padded to the UMMA N)
+int conv_halo_final_fwd(const void* h, const void* wg, const float* bias, const float* target, float* recon,
                         double* lpart, int* n_lpart, int loss_type, int B, int H, int W, int C, int Co, cudaStream_t st);
 
 // ---- final conv backward on tcgen05 (finalconv_tc.cu): C = 64 -> 1 channel ----

@@ -52,11 +52,6 @@ struct HaloParams {
   uint32_t a_off, b_off, bar_off;
   __nv_bfloat16* dst;
   const float* bias;
-  // EPI == 1 (final_conv + sigmoid + reconstruction loss, src/models/beta_vae.py:163-164,185-192)
-  const float* target;     // [B][Co][H][W] fp32 or null
-  float* recon;            // [B][Co][H][W] fp32
-  double* lpart;           // [gridDim.x * 4] per-warp partial sums of the elementwise loss, or null
-  int loss_type, Co;
 };
 
 struct HaloMaps {
@@ -91,7 +86,7 @@ __device__ __forceinline__ float final_elem_loss(float r, float x, int type) {
 // Window j = (r, s) of the halo starts ((r * 10) + s) pixel rows into the buffer.  fprop uses weight tap j with
 // window j; dgrad (flipped kernel) uses weight tap 8 - j with window j -- the producer stores tap `wtap(j)` in
 // weight slot j, so the MMA loop is identical for both and fully unrolled with constant offsets.
-template <int BN, bool RESIDENT, int EPI>
+template <int BN, bool RESIDENT>
 __global__ void __launch_bounds__(HL_THREADS, 1)
     conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -128,7 +123,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
     mbar_init(b_res, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.N; i += HL_THREADS) bias_sm[i] = (p.bias && (EPI == 0 || i < p.Co)) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.N; i += HL_THREADS) bias_sm[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -241,7 +236,6 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
     const int r = q * 32 + lane;            // pixel inside the 16x8 tile
     const int hl = r / HL_TW, wl = r % HL_TW;
     uint32_t iu = 0;
-    float lsum = 0.f;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const int nt = u % p.n_tiles, mg = u / p.n_tiles;
       const int n0 = nt * BN;
@@ -256,21 +250,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
         const int h0 = (mt % p.tiles_h) * HL_TH;
         const int b = mt / p.tiles_h;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.tm * BN) + (uint32_t)(m * BN);
-        if constexpr (EPI == 1) {
-          // columns 0..Co-1 hold the logits; sigmoid, write recon (NCHW fp32), accumulate the loss
-          uint32_t v[16];
-          tmem_ld16(taddr, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int co = 0; co < 3; ++co) {
-            if (co >= p.Co) break;
-            const float logit = __uint_as_float(v[co]) + bias_sm[co];
-            const float rr = 1.f / (1.f + expf(-logit));
-            const size_t o = (((size_t)b * p.Co + co) * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl);
-            p.recon[o] = rr;
-            if (p.target) lsum += final_elem_loss(rr, p.target[o], p.loss_type);
-          }
-        } else {
+        {
           __nv_bfloat16* out = p.dst + (((size_t)b * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl)) * p.N + n0;
 #pragma unroll 1
           for (int c = 0; c < BN; c += 32) {
@@ -298,12 +278,6 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-    }
-    if constexpr (EPI == 1) {
-      if (p.lpart) {
-        const double s = warp_sum((double)lsum);
-        if (lane == 0) p.lpart[blockIdx.x * 4 + q] = s;
-      }
     }
   }
   tc_fence_before();
@@ -402,8 +376,8 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
     if (grid < p.n_tiles) grid = p.n_tiles;
   }
   void (*kern)(const HaloMaps, const HaloParams) = nullptr;
-  if (p.resident) kern = p.bn == 64 ? conv_halo_tc_kernel<64, true, 0> : (p.bn == 128 ? conv_halo_tc_kernel<128, true, 0> : conv_halo_tc_kernel<256, true, 0>);
-  else            kern = p.bn == 64 ? conv_halo_tc_kernel<64, false, 0> : (p.bn == 128 ? conv_halo_tc_kernel<128, false, 0> : conv_halo_tc_kernel<256, false, 0>);
+  if (p.resident) kern = p.bn == 64 ? conv_halo_tc_kernel<64, true> : (p.bn == 128 ? conv_halo_tc_kernel<128, true> : conv_halo_tc_kernel<256, true>);
+  else            kern = p.bn == 64 ? conv_halo_tc_kernel<64, false> : (p.bn == 128 ? conv_halo_tc_kernel<128, false> : conv_halo_tc_kernel<256, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX);
   if (e != cudaSuccess) return cuda_fail(e, "conv_halo: cudaFuncSetAttribute");
   kern<<<grid, HL_THREADS, smem, st>>>(maps, p);
@@ -411,40 +385,228 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
   return BVAE_OK;
 }
 
-// final_conv (C -> Co <= 3) + sigmoid + reconstruction loss on the same halo pipeline: the output-channel
-// dimension is padded to the smallest UMMA N (16) -- `wp16` is the [9][16][C] bf16 pack with zero rows
-// beyond Co -- and the epilogue reads the Co logit columns straight from TMEM.
+// ------------------------------------------------------------------------------------------
+// final_conv (C -> Co <= 3) + sigmoid + reconstruction loss  (src/models/beta_vae.py:163-164,185-192)
+//
+// With one to three output channels the tap-by-tap implicit GEMM would issue nine N = 16 MMAs per K step whose cost is
+// all A-operand fetch.  Here the channel contraction is done ONCE per halo pixel for all nine taps,
+//     G[hp][t * Co + co] = sum_c halo[hp][c] * w[co][c][t]          (N = 9 * Co padded to 16 / 32),
+// as two M = 128 MMAs per K step over the 180 halo rows read as a dense K-major tile (rows 0..127 and 52..179; the
+// second start is not swizzle-atom aligned, which the UMMA address swizzle handles -- see the header of this file), and
+// the 3x3 spatial sum is a nine-term stencil over G in the epilogue:
+//     logit[p][co] = bias[co] + sum_t G[p + off_t][t * Co + co].
+// 4.5x fewer MMAs than tap-by-tap; the kernel is bound by the single read of h.
+// Epilogue warps: TMEM -> G in shared memory (double buffered) -> named barrier -> stencil + sigmoid + loss.
+// ------------------------------------------------------------------------------------------
+static constexpr int FG_HALO_PX = HL_HH * HL_HW;   // 180
+static constexpr int FG_ROW2 = FG_HALO_PX - 128;   // 52: first halo row of the second MMA
+
+struct FinalGsParams {
+  int kchunks, tiles_w, tiles_h, units;
+  int B, H, W, Co, nt;       // nt = 9 * Co
+  int sa;
+  uint32_t a_off, g_off, bar_off;
+  const float* bias;
+  const float* target;       // [B][Co][H][W] fp32 or null
+  float* recon;              // [B][Co][H][W] fp32
+  double* lpart;             // [gridDim.x * 4] or null
+  int loss_type;
+};
+
+template <int N>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+    finalconv_gs_kernel(const __grid_constant__ HaloMaps maps, const FinalGsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_base = smem;                                  // [kchunks][N][64] bf16, 128B-swizzled rows
+  uint8_t* a_ring = smem + p.a_off;
+  float* g_sm = reinterpret_cast<float*>(smem + p.g_off);  // [2][180][nt]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* a_empty = a_full + p.sa;
+  uint64_t* acc_full = a_empty + p.sa;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_res = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
+  constexpr uint32_t TMEM_COLS = 4 * N;                    // two accumulators per buffer, two buffers
+  constexpr uint32_t B_CHUNK = (uint32_t)N * HL_ROW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.sa; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_init(b_res, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.x);
+      tma_prefetch_desc(&maps.w);
+      mbar_expect_tx(b_res, (uint32_t)p.kchunks * B_CHUNK);
+      for (int c = 0; c < p.kchunks; ++c) tma_load_3d(&maps.w, b_res, b_base + (size_t)c * B_CHUNK, c * 64, 0, 0);
+      uint32_t ia = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        int mt = u;
+        const int w0 = (mt % p.tiles_w) * HL_TW;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * HL_TH;
+        const int b = mt / p.tiles_h;
+        for (int c = 0; c < p.kchunks; ++c, ++ia) {
+          const uint32_t sa = ia % p.sa;
+          mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[sa], HL_HALO_BYTES);
+          tma_load_4d(&maps.x, &a_full[sa], a_ring + (size_t)sa * HL_HALO_SLOT, c * 64, w0 - 1, h0 - 1, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc =
+          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(b_res, 0);
+      tc_fence_after();
+      uint32_t ia = 0, iu = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+        const uint32_t buf = iu & 1u;
+        mbar_wait(&acc_empty[buf], ((iu >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * (uint32_t)(2 * N);
+        for (int c = 0; c < p.kchunks; ++c, ++ia) {
+          const uint32_t sa = ia % p.sa;
+          mbar_wait(&a_full[sa], (ia / p.sa) & 1u);
+          tc_fence_after();
+          const uint64_t a_desc0 = kmajor_desc(smem_u32(a_ring + (size_t)sa * HL_HALO_SLOT), HL_ROW);   // dense rows
+          const uint64_t b_desc0 = kmajor_desc(smem_u32(b_base + (size_t)c * B_CHUNK), HL_ROW);
+          const uint32_t acc_on = c != 0 ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(acc, a_desc0 + (uint64_t)((k * 32) >> 4), b_desc0 + (uint64_t)(k * 2), idesc, k != 0 ? 1u : acc_on);
+            umma_bf16(acc + N, a_desc0 + (uint64_t)((FG_ROW2 * HL_ROW + k * 32) >> 4), b_desc0 + (uint64_t)(k * 2), idesc,
+                      k != 0 ? 1u : acc_on);
+          }
+          umma_commit(&a_empty[sa]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;            // TMEM lane = halo row (first MMA) / halo row - 52 (second); also the output pixel
+    const int hl = r / HL_TW, wl = r % HL_TW;
+    const int nt = p.nt;
+    uint32_t iu = 0;
+    float lsum = 0.f;
+    float bias_r[3];
+#pragma unroll
+    for (int co = 0; co < 3; ++co) bias_r[co] = (p.bias && co < p.Co) ? p.bias[co] : 0.f;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      int mt = u;
+      const int w0 = (mt % p.tiles_w) * HL_TW;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * HL_TH;
+      const int b = mt / p.tiles_h;
+      const uint32_t buf = iu & 1u;
+      float* g = g_sm + (size_t)buf * FG_HALO_PX * nt;
+      // the target pixel is fetched before waiting on the accumulator so its DRAM latency is off the per-tile chain
+      const size_t o0 = ((size_t)b * p.Co * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl);
+      const size_t plane = (size_t)p.H * p.W;
+      float tgt[3] = {0.f, 0.f, 0.f};
+      if (p.target) {
+#pragma unroll
+        for (int co = 0; co < 3; ++co)
+          if (co < p.Co) tgt[co] = __ldg(p.target + o0 + (size_t)co * plane);
+      }
+      mbar_wait(&acc_full[buf], (iu >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(2 * N);
+      {
+        uint32_t v[N], v2[N];
+        if constexpr (N == 16) {
+          tmem_ld16(taddr, v);
+          tmem_ld16(taddr + N, v2);
+        } else {
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + N, v2);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        float* g1 = g + (size_t)r * nt;
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+          if (n < nt) g1[n] = __uint_as_float(v[n]);
+        if (r >= 128 - FG_ROW2) {            // halo rows 128..179 come from the second accumulator
+          float* g2 = g + (size_t)(r + FG_ROW2) * nt;
+#pragma unroll
+          for (int n = 0; n < N; ++n)
+            if (n < nt) g2[n] = __uint_as_float(v2[n]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);          // accumulators are in registers / shared memory now
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // G of this tile complete (epilogue warps only)
+#pragma unroll
+      for (int co = 0; co < 3; ++co) {
+        if (co >= p.Co) break;
+        float logit = bias_r[co];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) logit += g[(size_t)((hl + t / 3) * HL_HW + wl + t % 3) * nt + t * p.Co + co];
+        const float rr = 1.f / (1.f + expf(-logit));
+        p.recon[o0 + (size_t)co * plane] = rr;
+        if (p.target) lsum += final_elem_loss(rr, tgt[co], p.loss_type);
+      }
+    }
+    if (p.lpart) {
+      const double s = warp_sum((double)lsum);
+      if (lane == 0) p.lpart[blockIdx.x * 4 + q] = s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 bool conv_halo_final_supported(int H, int W, int C, int Co) {
   if (getenv("BVAE_CONV_NO_HALO")) return false;
   return H % HL_TH == 0 && W % HL_TW == 0 && C % 64 == 0 && C <= 256 && Co >= 1 && Co <= 3;
 }
 
-int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, const float* target, float* recon,
+int conv_halo_final_rows(int Co) { return Co == 1 ? 16 : 32; }
+
+// wg = [rows][C] bf16 with row t * Co + co = w[co][:][t] (rows >= 9 * Co zero), rows = conv_halo_final_rows(Co)
+int conv_halo_final_fwd(const void* h, const void* wg, const float* bias, const float* target, float* recon,
                         double* lpart, int* n_lpart, int loss_type, int B, int H, int W, int C, int Co,
                         cudaStream_t st) {
   HaloMaps maps;
-  HaloParams p;
+  FinalGsParams p;
   memset(&p, 0, sizeof(p));
+  const int N = conv_halo_final_rows(Co);
   p.kchunks = C / 64;
   p.tiles_w = W / HL_TW;
   p.tiles_h = H / HL_TH;
-  p.m_tiles = p.tiles_w * p.tiles_h * B;
-  p.B = B; p.H = H; p.W = W; p.N = 16;
+  p.units = p.tiles_w * p.tiles_h * B;
+  p.B = B; p.H = H; p.W = W; p.Co = Co; p.nt = 9 * Co;
   p.bias = bias;
-  p.target = target; p.recon = recon; p.lpart = lpart; p.loss_type = loss_type; p.Co = Co;
-  p.resident = 1; p.bn = 16; p.tm = 1; p.sb = 0; p.n_tiles = 1;
-  const size_t bar_bytes = 256 + 16 * sizeof(float) + 64;
-  const size_t wbytes = (size_t)9 * C * 16 * 2;
-  int sa = (int)((HL_SMEM_MAX - 1024 - bar_bytes - wbytes) / HL_HALO_SLOT);
-  p.sa = sa > 8 ? 8 : sa;
-  p.b_off = 0;
-  p.a_off = (uint32_t)align_up(wbytes, 1024);
-  p.bar_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;
+  p.target = target; p.recon = recon; p.lpart = lpart; p.loss_type = loss_type;
+  const size_t wbytes = align_up((size_t)p.kchunks * N * HL_ROW, 1024);
+  const size_t gbytes = align_up((size_t)2 * FG_HALO_PX * p.nt * sizeof(float), 1024);
+  const size_t bar_bytes = 512;
+  int sa = (int)((HL_SMEM_MAX - 1024 - bar_bytes - wbytes - gbytes) / HL_HALO_SLOT);
+  p.sa = sa > 6 ? 6 : sa;
+  p.a_off = (uint32_t)wbytes;
+  p.g_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;
+  p.bar_off = p.g_off + (uint32_t)gbytes;
   const size_t smem = 1024 + p.bar_off + bar_bytes;
-  p.m_groups = p.m_tiles;
-  p.units = p.m_tiles;
-  p.nbuf = 2;
-  p.tmem_cols = 32;
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
@@ -453,19 +615,19 @@ int conv_halo_final_fwd(const void* h, const void* wp16, const float* bias, cons
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)C, 16, 9};
-    const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)C * 16 * 2};
-    const uint32_t box[3] = {64u, 16u, 1u};
-    int rc = make_map(&maps.w, wp16, 3, dims, strides, box, 128);
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, 1};
+    const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)C * N * 2};
+    const uint32_t box[3] = {64u, (uint32_t)N, 1u};
+    int rc = make_map(&maps.w, wg, 3, dims, strides, box, 128);
     if (rc) return rc;
   }
   const int sms = num_sms();
   const int grid = p.units < sms ? p.units : sms;
-  auto kern = conv_halo_tc_kernel<16, true, 1>;
+  auto kern = N == 16 ? finalconv_gs_kernel<16> : finalconv_gs_kernel<32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX);
   if (e != cudaSuccess) return cuda_fail(e, "conv_halo_final: cudaFuncSetAttribute");
   kern<<<grid, HL_THREADS, smem, st>>>(maps, p);
-  BVAE_LAUNCH_CHECK("conv_halo_final_fwd");
+  BVAE_LAUNCH_CHECK("finalconv_gs");
   *n_lpart = grid * 4;
   return BVAE_OK;
 }

@@ -123,6 +123,41 @@ __global__ void pack_fcdec_kernel(const float* __restrict__ w, const float* __re
   }
 }
 
+// Both packs above are batched [R x Q] -> [Q x R] transposes; with R = C even they go through a 64 x 32 shared-memory
+// tile so that reads (Q contiguous, fp32) and writes (R contiguous, two elements per lane = 128 B per warp row) are
+// both coalesced.  The element-per-thread kernels above remain for odd shapes.
+//   dst[b * dbs + q * dcs + r] = src_b[r * srs + q],   src_b = (b < split ? src0 + b * sbs : src1 + (b - split) * sbs)
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    pack_transpose_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int split, T* __restrict__ dst,
+                          int R, int Q, long long srs, long long sbs, long long dcs, long long dbs,
+                          const float* __restrict__ bias, float* __restrict__ bias_out) {
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, r0 = blockIdx.y * 64, q0 = blockIdx.x * 32;
+  const float* src = (b < split) ? src0 + (size_t)b * sbs : src1 + (size_t)(b - split) * sbs;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + ty + 8 * k, q = q0 + tx;
+    tile[ty + 8 * k][tx] = (r < R && q < Q) ? src[(size_t)r * srs + q] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int q = q0 + ty + 8 * k, r = r0 + 2 * tx;
+    if (q < Q && r < R)   // R is even: the pair (r, r + 1) is inside together
+      store2(dst + (size_t)b * dbs + (size_t)q * dcs + r, tile[2 * tx][ty + 8 * k], tile[2 * tx + 1][ty + 8 * k]);
+  }
+  // fc_dec bias rides along: bias_out[b * R + r] = bias[r * gridDim.z + b]   (b = pixel, r = channel)
+  if (bias_out != nullptr && blockIdx.x == 0 && threadIdx.x < 64 && r0 + (int)threadIdx.x < R)
+    bias_out[(size_t)b * R + r0 + threadIdx.x] = bias[(size_t)(r0 + threadIdx.x) * gridDim.z + b];
+}
+
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int C, int HW) {
   const long long total = (long long)B * C * HW;
@@ -272,6 +307,20 @@ extern "C" int bvae_pack_heads_weight(const float* w_mu, const float* w_logvar, 
                                       int dtype, bvae_stream_t stream) {
   BVAE_REQUIRE(w_mu && w_logvar && wh && L > 0 && C > 0 && P > 0, BVAE_ERR_ARG, "pack_heads_weight: bad argument");
   const long long total = 2LL * L * C * P;
+  if (C % 2 == 0 && 2 * L <= 65535) {   // batch = row of wh, [C x P] -> [P x C]
+    const dim3 grid((P + 31) / 32, (C + 63) / 64, 2 * L);
+    const long long F = (long long)C * P;
+    if (dtype == BVAE_F32)
+      pack_transpose_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w_mu, w_logvar, L, (float*)wh, C, P, P, F, C, F,
+                                                                       nullptr, nullptr);
+    else if (dtype == BVAE_BF16)
+      pack_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(w_mu, w_logvar, L, (__nv_bfloat16*)wh, C,
+                                                                               P, P, F, C, F, nullptr, nullptr);
+    else
+      BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_heads_weight: dtype %d", dtype);
+    BVAE_LAUNCH_CHECK("pack_heads_weight");
+    return BVAE_OK;
+  }
   if (dtype == BVAE_F32)
     pack_heads_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(w_mu, w_logvar, (float*)wh, L, C, P);
   else if (dtype == BVAE_BF16)
@@ -287,6 +336,20 @@ extern "C" int bvae_pack_fcdec_weight(const float* w, const float* b, void* wd, 
                                       int dtype, bvae_stream_t stream) {
   BVAE_REQUIRE(w && b && wd && bd && L > 0 && C > 0 && P > 0, BVAE_ERR_ARG, "pack_fcdec_weight: bad argument");
   const long long total = (long long)L * C * P;
+  if (C % 2 == 0 && P <= 65535) {   // batch = pixel p, [C x L] (row stride P*L) -> [L x C] (row stride F)
+    const dim3 grid((L + 31) / 32, (C + 63) / 64, P);
+    const long long F = (long long)C * P;
+    if (dtype == BVAE_F32)
+      pack_transpose_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w, w, P, (float*)wd, C, L, (long long)P * L, L, F,
+                                                                       C, b, bd);
+    else if (dtype == BVAE_BF16)
+      pack_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(w, w, P, (__nv_bfloat16*)wd, C, L,
+                                                                               (long long)P * L, L, F, C, b, bd);
+    else
+      BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "pack_fcdec_weight: dtype %d", dtype);
+    BVAE_LAUNCH_CHECK("pack_fcdec_weight");
+    return BVAE_OK;
+  }
   if (dtype == BVAE_F32)
     pack_fcdec_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(w, b, (float*)wd, bd, L, C, P);
   else if (dtype == BVAE_BF16)

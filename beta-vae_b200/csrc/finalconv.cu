@@ -264,7 +264,7 @@ struct FinalWs {
   float* dlogit;  // [B][Co][H][W]
   float* wpart;   // [kFcMaxCtas][Co][9][C]
   float* bpart;   // [kFcMaxCtas][Co]
-  __nv_bfloat16* wp16;  // [9][16][C] bf16 weights for the tcgen05 forward (rows >= Co are zero)
+  __nv_bfloat16* wp16;  // tcgen05 forward weights: [rows <= 32][C] bf16 (conv_halo_final_rows); sized 9*16*C
   void* dcol;           // tcgen05 backward: bf16 im2col of dlogit [B][H][W][16] + packed weights
   size_t bytes;
 };
@@ -287,13 +287,13 @@ static FinalWs final_ws_carve(void* base, int B, int H, int W, int C, int Co) {
   return w;
 }
 
-// w [Co][C][3][3] fp32 -> wp16 [9][16][C] bf16, zero rows for co >= Co
-__global__ void __launch_bounds__(256) final_pack16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
-                                                           int C, int Co) {
-  const int total = 9 * 16 * C;
+// w [Co][C][3][3] fp32 -> wg [rows][C] bf16 with row t * Co + co = w[co][:][t]; rows beyond 9 * Co are zero
+__global__ void __launch_bounds__(256) final_pack_g_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wg,
+                                                           int C, int Co, int rows) {
+  const int total = rows * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % C, co = (i / C) % 16, t = i / (16 * C);
-    wp[i] = __float2bfloat16_rn(co < Co ? w[((size_t)co * C + c) * 9 + t] : 0.f);
+    const int c = i % C, n = i / C, t = n / Co, co = n % Co;
+    wg[i] = __float2bfloat16_rn(n < 9 * Co ? w[((size_t)co * C + c) * 9 + t] : 0.f);
   }
 }
 
@@ -314,9 +314,11 @@ static int final_fwd_impl(const void* h, const float* w, const float* b, const f
   BVAE_REQUIRE(sm <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "finalconv: C=%d too large", C);
   const bool want_loss = target != nullptr && loss_out != nullptr;
   if (sizeof(T) == 2 && !final_tc_env_off() && conv_halo_final_supported(H, W, C, Co)) {
-    // tcgen05 path: the 3x3xC contraction runs on the tensor cores (N padded to 16), fused epilogue
-    final_pack16_kernel<<<cdiv(9 * 16 * C, 256), 256, 0, st>>>(w, fw.wp16, C, Co);
-    BVAE_LAUNCH_CHECK("final_pack16");
+    // tcgen05 path: channel contraction for all nine taps at once on the tensor cores, 3x3 stencil + sigmoid + loss
+    // in the epilogue (conv_tc_halo.cu)
+    const int rows = conv_halo_final_rows(Co);
+    final_pack_g_kernel<<<cdiv(rows * C, 256), 256, 0, st>>>(w, fw.wp16, C, Co, rows);
+    BVAE_LAUNCH_CHECK("final_pack_g");
     int n_lpart = 0;
     const int rc = conv_halo_final_fwd(h, fw.wp16, b, want_loss ? target : nullptr, recon, want_loss ? fw.lpart : nullptr,
                                        &n_lpart, loss_type, B, H, W, C, Co, st);

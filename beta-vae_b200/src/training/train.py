@@ -109,6 +109,24 @@ def _payload(model, engine, epoch, total_steps, val_total):
     }
 
 
+def _staged_images(loader, step_fn):
+    """The loader's image batches, one step ahead: when batch i is handed to the step, the host->device copy of batch
+    i+1 is already running on the copy stream (GraphedTrainStep.prefetch).  Without a graphed step, or for batches
+    that already live on the device, the tensors pass through unchanged."""
+    prev = None
+    for batch_d in loader:
+        x = batch_d["image"]
+        if isinstance(x, (list, tuple)):
+            x = torch.stack(x, 0)
+        if step_fn is not None and not x.is_cuda and tuple(x.shape) == tuple(step_fn.x.shape):
+            x = step_fn.prefetch(x)
+        if prev is not None:
+            yield prev
+        prev = x
+    if prev is not None:
+        yield prev
+
+
 def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_graph=True):
     cfg = cfg or get_config()
     distributed = dist.is_available() and dist.is_initialized()
@@ -187,10 +205,7 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
         running = torch.zeros(6, device=device)     # total, recon, recon_base, recon_lpips, recon_ffl, kl
         last = None
         n_batches = 0
-        for i, batch_d in enumerate(train_loader):
-            x = batch_d["image"]
-            if isinstance(x, (list, tuple)):
-                x = torch.stack(x, 0)
+        for i, x in enumerate(_staged_images(train_loader, step_fn)):
             engine.lr = _lr_at(cfg, epochs, epoch - 1, total_steps)
             if step_fn is not None:
                 losses = step_fn(x, **kw)
