@@ -193,7 +193,7 @@ def cuda_main(args):
     if world > 1:
         dist.barrier()
 
-    from bvae_rt import lib, profiler
+    from bvae_rt import lib, ops, profiler
     from bvae_rt.data import synthetic_batch
     from bvae_rt.engine import GraphedTrainStep, TrainEngine
     from models.beta_vae import BetaVAE
@@ -265,7 +265,10 @@ def cuda_main(args):
     value = world * batch * args.steps / (ms / 1e3)
 
     # ---- (2) end to end through the public API with host buffers
-    host = [x.cpu().pin_memory() for x in xs]
+    # the dataset's native format: uint8 image bytes (the reference decodes PNGs to bytes and ToTensor divides by 255);
+    # they cross PCIe as bytes and become the same fp32 values on the device (bvae_u8_to_unit_f32, bit-exact)
+    host = [(x * 255.0).round().to(torch.uint8).cpu().pin_memory() for x in xs]
+    assert torch.equal(ops.u8_to_unit_f32(host[0].to(dev)), xs[0]), "uint8 round trip of the synthetic batch is not exact"
     xdev = torch.empty_like(xs[0])
     host_out = torch.empty(4, dtype=torch.float32).pin_memory()
 
@@ -278,7 +281,7 @@ def cuda_main(args):
             out = train_step(staged[0])
             staged[0] = graphed.prefetch(host[(i + 1) % n_batches])
         else:
-            xdev.copy_(host[i % n_batches], non_blocking=True)
+            ops.u8_to_unit_f32(host[i % n_batches].to(dev, non_blocking=True), xdev)
             out = train_step(xdev)
         scal[0], scal[1], scal[2], scal[3] = out["total"].detach(), out["recon"].detach(), out["kl_mean"].detach(), \
             out["recon_ffl"]
@@ -418,7 +421,8 @@ def cuda_main(args):
                              f"input batches, above the 126 MB L2"},
             "clocks": clk.result(),
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": xs[0].numel() * 4, "d2h_bytes_per_step": 16},
+                    "h2d_bytes_per_step": host[0].numel() * host[0].element_size(), "d2h_bytes_per_step": 16,
+                    "input": "pinned uint8 image bytes, prefetched on a copy stream, /255 on the device"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_more": more,
@@ -440,7 +444,7 @@ def cuda_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: training.batch_size of the config)")

@@ -25,5 +25,7 @@ def synthetic_batch(n: int, size: int, seed: int = 0, device="cuda", in_ch: int 
     add += (cls == 1).view(n, 1, 1) * (0.25 * bands)
     add += (cls == 2).view(n, 1, 1) * (0.25 * hatch)
     add += (cls == 3).view(n, 1, 1) * extra
-    img = torch.floor((canvas + add).clamp_(0, 1) * 255.0) / 255.0
+    # divide by a device tensor, not a Python scalar: ATen turns `x / scalar` on CUDA into x * (1 / scalar), which is
+    # 1 ulp off ToTensor's (CPU, IEEE) byte / 255 for half of the 256 levels
+    img = torch.floor((canvas + add).clamp_(0, 1) * 255.0) / torch.full((), 255.0, device=dev)
     return img.view(n, 1, size, size).expand(n, in_ch, size, size).contiguous()

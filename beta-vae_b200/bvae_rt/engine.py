@@ -301,10 +301,12 @@ class GraphedTrainStep:
     def prefetch(self, x) -> "StagedBatch":
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.engine.device)
-            self._stage = [torch.empty_like(self.x) for _ in range(2)]
+            self._stage = {}
+        if x.dtype not in self._stage:               # fp32 images, or uint8 bytes (converted on the device: x / 255)
+            self._stage[x.dtype] = [torch.empty(self.x.shape, dtype=x.dtype, device=self.x.device) for _ in range(2)]
         slot = self._slot
         self._slot ^= 1
-        buf = self._stage[slot]
+        buf = self._stage[x.dtype][slot]
         cs = self._copy_stream
         if self._consumed[slot] is not None:
             cs.wait_event(self._consumed[slot])      # the step that read this buffer two batches ago
@@ -318,10 +320,15 @@ class GraphedTrainStep:
         if isinstance(x, StagedBatch):
             cur = torch.cuda.current_stream()
             cur.wait_event(x.ready)
-            self.x.copy_(x.buf, non_blocking=True)   # device-to-device into the graph's static input
+            if x.buf.dtype == torch.uint8:
+                ops.u8_to_unit_f32(x.buf, self.x)    # bytes -> ToTensor's floats, into the graph's static input
+            else:
+                self.x.copy_(x.buf, non_blocking=True)   # device-to-device into the graph's static input
             done = torch.cuda.Event()
             done.record(cur)
             self._consumed[x.slot] = done
+        elif x.dtype == torch.uint8:
+            ops.u8_to_unit_f32(x.to(self.x.device, non_blocking=True).contiguous(), self.x)
         else:
             self.x.copy_(x, non_blocking=True)
 

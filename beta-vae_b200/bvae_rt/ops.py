@@ -181,6 +181,14 @@ def nchw_to_nhwc(x, dt):
     return y
 
 
+def u8_to_unit_f32(src, out=None):
+    """uint8 CUDA tensor -> fp32 / 255 (ToTensor's values, bit-exact); ``out`` may be a preallocated fp32 tensor."""
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    call("bvae_u8_to_unit_f32", _p(src), _p(out), src.numel(), _stream())
+    return out
+
+
 def conv3x3_fprop(x, wp, bias, cout, stride, dt):
     B, H, W, Cin = x.shape
     y = torch.empty((B, conv_out(H, stride), conv_out(W, stride), cout), dtype=torch_dtype(dt), device=x.device)

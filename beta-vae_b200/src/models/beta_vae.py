@@ -190,7 +190,8 @@ class BetaVAE(nn.Module):
     def _nhwc_input(self, x):
         if not x.is_cuda:
             raise RuntimeError("BetaVAE (bvae_b200) runs on CUDA tensors only; there is no CPU path")
-        x = x.contiguous().float()
+        # uint8 images (the dataset's PNG bytes) become ToTensor's floats on the device: x / 255, bit-exact
+        x = ops.u8_to_unit_f32(x.contiguous()) if x.dtype == torch.uint8 else x.contiguous().float()
         b, c, h, w = x.shape
         return x.view(b, h, w, 1) if c == 1 else ops.nchw_to_nhwc(x, F32)
 

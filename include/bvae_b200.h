@@ -216,6 +216,11 @@ int bvae_ffl_fwd(const float* spec, int B, int C, int H, int Wh, int W, float al
 int bvae_ffl_bwd(const float* spec, const float* scale, const float* U, const float* g_loss, float* g_spec, int B,
                  int C, int H, int Wh, int W, float alpha, float eps, bvae_stream_t stream);
 
+/* Input pipeline: uint8 image bytes -> fp32 in [0, 1], dst[i] = float(src[i]) / 255 with IEEE division -- the values
+ * torchvision's ToTensor produces from the dataset's PNGs (datautils.py:59-65), so shipping bytes over PCIe and
+ * converting on the device is bit-identical to shipping ToTensor's floats.  n = element count; 16-byte aligned. */
+int bvae_u8_to_unit_f32(const void* src, float* dst, size_t n, bvae_stream_t stream);
+
 /* NCHW fp32 -> NHWC act dtype (RGB input path, data.grayscale: false) and back. */
 int bvae_nchw_to_nhwc(const float* x, void* y, int B, int C, int H, int W, int dtype, bvae_stream_t stream);
 

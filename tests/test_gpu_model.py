@@ -226,3 +226,56 @@ def test_graphed_train_step_matches_eager_engine():
         assert abs(lg - float(lo)) <= 2e-5 * abs(float(lo)), (lg, float(lo))
     for k, v in m.state_dict().items():
         assert rel_err(v, sd[k]) <= 5e-2, k
+
+
+def test_graphed_step_prefetched_uint8_input_is_bit_identical():
+    """Input pipeline: pinned uint8 image bytes, copied on the copy stream one step ahead
+    (GraphedTrainStep.prefetch) and divided by 255 on the device, drive the step to exactly the losses that
+    ToTensor's fp32 values passed directly give -- eager steps and graph replays alike."""
+    from bvae_rt.engine import GraphedTrainStep, TrainEngine
+    import cfgs
+    cfg = cfgs.small(loss__use_ffl=True, loss__ffl_weight=0.5)
+    torch.manual_seed(3)
+    ref = build_model(cfg, None, "fp32")
+    state = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    kw = dict(beta=1.0, capacity=3.0, free_bits=0.0, capacity_weight=1.0)
+    g = torch.Generator().manual_seed(5)
+    u8 = [torch.randint(0, 256, (4, 1, 32, 32), generator=g, dtype=torch.uint8).pin_memory() for _ in range(6)]
+    eps = [torch.randn(4, 8, generator=g).cuda() for _ in range(6)]
+    runs = []
+    for mode in ("float", "staged-u8", "direct-u8"):
+        m = build_model(cfg, state, "fp32")
+        eng = TrainEngine(m, lr=2e-3, clip=3.0)
+        step = GraphedTrainStep(eng, (4, 1, 32, 32), autocast_dtype=None, eager_steps=2)
+        losses = []
+        try:
+            staged = step.prefetch(u8[0]) if mode == "staged-u8" else None
+            for i in range(6):
+                if mode == "float":
+                    x = u8[i].float().div(255).cuda()          # torchvision ToTensor on the host
+                elif mode == "staged-u8":
+                    x = staged
+                else:
+                    x = u8[i]
+                out = step(x, eps=eps[i], **kw)
+                if mode == "staged-u8" and i + 1 < 6:
+                    staged = step.prefetch(u8[i + 1])          # next batch in flight while this step runs
+                losses.append(float(out["total"]))
+            assert step.graph is not None
+        finally:
+            eng.close()
+        runs.append(losses)
+    assert runs[0] == runs[1] == runs[2], runs
+
+
+def test_encode_accepts_uint8_images():
+    import cfgs
+    cfg = cfgs.small()
+    torch.manual_seed(3)
+    m = build_model(cfg, None, "fp32").eval()
+    g = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (5, 1, 32, 32), generator=g, dtype=torch.uint8)
+    with torch.no_grad():
+        mu_a, lv_a = m.encode(u8.cuda())
+        mu_b, lv_b = m.encode(u8.float().div(255).cuda())
+    assert torch.equal(mu_a, mu_b) and torch.equal(lv_a, lv_b)

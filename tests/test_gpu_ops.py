@@ -447,3 +447,12 @@ def test_conv_first_layer_tcgen05(B, size):
     dw, db = ops.conv_first_wgrad(xcol, nhwc(dy, torch.bfloat16))
     assert rel_err(dw, wr.grad) <= 5e-4          # fp32 accumulation of bf16 products
     assert rel_err(db, br.grad) <= 5e-4
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 4099, 32 * 128 * 128])
+def test_u8_to_unit_f32_matches_totensor(n):
+    ops = _ops()
+    g = torch.Generator().manual_seed(n)
+    u8 = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+    got = ops.u8_to_unit_f32(u8.to(dev()))
+    assert torch.equal(got.cpu(), u8.float().div(255))       # bit-exact: IEEE division, as ToTensor

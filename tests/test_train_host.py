@@ -171,3 +171,19 @@ def test_gradient_buckets_all_reduce_over_two_gloo_ranks():
         p.join(180)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert dict(out) == {0: "ok", 1: "ok"}
+
+
+def test_inference_latent_sequences_match_reference_loops():
+    """generate.py's batched latent matrices are the rows the reference builds one Python iteration at a time
+    (reference: src/inference/generate.py:41-46, 55-59)."""
+    from inference import generate as G
+    g = torch.Generator().manual_seed(1)
+    mu = torch.randn(2, 8, generator=g)
+    z = G.edit_latents(mu[:1], 3, 5, 3.0)
+    for i, v in enumerate(torch.linspace(-3.0, 3.0, 5)):
+        ref = mu[:1].clone()
+        ref[:, 3] = v
+        assert torch.equal(z[i:i + 1], ref)
+    zi = G.interpolation_latents(mu[0:1], mu[1:2], 6)
+    for i, a in enumerate(torch.linspace(0, 1, 6)):
+        assert torch.equal(zi[i:i + 1], (1 - a) * mu[0:1] + a * mu[1:2])
