@@ -277,15 +277,18 @@ def cuda_main(args):
     def e2e_step(i):
         if graphed is not None:
             # this step's input was put in flight (pinned host -> device, copy stream) while the previous step ran;
-            # the next step's H2D is enqueued right behind this step's launch: one 2 MB H2D per step, overlapped
+            # the next step's H2D is enqueued right behind this step's launch: one H2D per step, overlapped
             out = train_step(staged[0])
             staged[0] = graphed.prefetch(host[(i + 1) % n_batches])
         else:
             ops.u8_to_unit_f32(host[i % n_batches].to(dev, non_blocking=True), xdev)
             out = train_step(xdev)
-        scal[0], scal[1], scal[2], scal[3] = out["total"].detach(), out["recon"].detach(), out["kl_mean"].detach(), \
-            out["recon_ffl"]
-        host_out.copy_(scal, non_blocking=True)                      # D2H of the step's loss scalars
+        if "scalars" in out:                                         # graphed step: packed inside the graph
+            host_out.copy_(out["scalars"], non_blocking=True)        # D2H of the step's loss scalars
+        else:
+            scal[0], scal[1], scal[2], scal[3] = out["total"].detach(), out["recon"].detach(), \
+                out["kl_mean"].detach(), out["recon_ffl"]
+            host_out.copy_(scal, non_blocking=True)
         torch.cuda.current_stream().synchronize()                    # the train loop reads them every step
         return float(host_out[0])
 

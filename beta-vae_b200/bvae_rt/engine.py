@@ -105,6 +105,8 @@ class TrainEngine:
         self._bucket_of = {n: i for i, b in enumerate(self.bucket_names) for n in b}
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._hyper = torch.zeros(4, dtype=torch.float32, device=dev)   # lr, 1-b1^t, sqrt(1-b2^t)
+        self._hyper_host = None      # pinned staging ring for _hyper (advance())
+        self._hyper_done = None
         self._ws = torch.empty(query("bvae_adam_workspace", self.numel), dtype=torch.uint8, device=dev)
         self._hooks = []
         arena = ops.GradArena()
@@ -175,8 +177,19 @@ class TrainEngine:
         Adam bias corrections) to the device buffer the graph-safe kernels read."""
         self.step_count += 1
         b1, b2 = self.betas
-        self._hyper.copy_(torch.tensor([self.lr, 1.0 - b1 ** self.step_count,
-                                        math.sqrt(1.0 - b2 ** self.step_count), 0.0], dtype=torch.float32))
+        # pinned staging ring: the copy is asynchronous, so a slot is rewritten only after the copy that last read it
+        if self._hyper_host is None:
+            self._hyper_host = torch.empty(8, 4, dtype=torch.float32).pin_memory()
+            self._hyper_done = [None] * 8
+        k = self.step_count % 8
+        if self._hyper_done[k] is not None:
+            self._hyper_done[k].synchronize()
+        h = self._hyper_host[k]
+        h[0], h[1], h[2], h[3] = self.lr, 1.0 - b1 ** self.step_count, math.sqrt(1.0 - b2 ** self.step_count), 0.0
+        self._hyper.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_done[k] = ev
 
     def step(self, from_device_scalars: bool = False):
         """Global-norm clip + Adam over the flat buffers.  Gradients are SUMS over ranks at this
@@ -343,7 +356,11 @@ class GraphedTrainStep:
         self.engine.step(from_device_scalars=True)
         # hand back plain tensors: a live autograd graph would pin this iteration's AccumulateGrad
         # nodes (and their stream) and break the capture that follows the eager steps
-        return {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+        res = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+        # the scalars a training loop logs, packed so one 16-byte device->host copy reads them all
+        res["scalars"] = torch.stack([res["total"].float(), res["recon"].float(), res["kl_mean"].float(),
+                                      res["recon_ffl"].float().to(res["total"].device)])
+        return res
 
     def _capture(self, kw):
         from .lib import query
