@@ -23,85 +23,94 @@ namespace bvae {
 // ------------------------------------------------------------------------------------------
 // reduce-F
 // ------------------------------------------------------------------------------------------
-static constexpr int RF_CHUNK = 128;  // features per CTA
+static constexpr int RF_CHUNK = 128;  // features per CTA (one fp32 partial [M][N] per chunk)
+static constexpr int RF_SUB = 64;     // features staged in shared memory per pass
 static constexpr int RF_MT = 32;      // rows (batch) per CTA
-static constexpr int RF_NT = 32;      // output columns per inner tile
-static constexpr int RF_LD = RF_CHUNK + 4;
+static constexpr int RF_NT = 128;     // output columns per pass
+static constexpr int RF_LDX = RF_MT + 4, RF_LDW = RF_NT + 4;
 
+// CTA tile 32 (m) x 128 (n) x 128 (f), thread tile 4 x 4.  Both operand tiles are stored TRANSPOSED in shared memory
+// ([f][m], [f][n]) so that one feature step is one broadcast 16-byte read of X and one conflict-free 16-byte read of W
+// per thread for 16 FMAs (the earlier [row][f] layout needed five 16-byte reads per 16 FMAs and ran at the
+// shared-memory pipe's limit).  Lanes map to rows when loading, so the transposed stores are conflict free.
 template <typename T>
 __global__ void __launch_bounds__(256) fc_reduce_f_kernel(const T* __restrict__ X, const T* __restrict__ Wm,
                                                           float* __restrict__ part, int M, int N, int F) {
-  __shared__ __align__(16) float Xs[RF_MT][RF_LD];
-  __shared__ __align__(16) float Ws[RF_NT][RF_LD];
+  __shared__ __align__(16) float Xs[RF_SUB][RF_LDX];
+  __shared__ __align__(16) float Ws[RF_SUB][RF_LDW];
   const int chunk = blockIdx.x, m0 = blockIdx.y * RF_MT;
   const int f0 = chunk * RF_CHUNK;
   const int tid = threadIdx.x;
-  // 16-byte loads when a tile row is vector aligned and fully inside F (the 2-byte scalar form was LSU bound)
   constexpr int V = Vec16<T>::N;
-  const bool vec_ok = (F % V == 0) && (f0 + RF_CHUNK <= F);
-  // X tile: 32 rows x RF_CHUNK features
-  if (vec_ok) {
-    for (int i = tid; i < RF_MT * (RF_CHUNK / V); i += 256) {
-      const int r = i / (RF_CHUNK / V), q = i % (RF_CHUNK / V);
-      Vec16<T> v;
-      if (m0 + r < M) {
-        v.load(X + (size_t)(m0 + r) * F + f0 + q * V);
+  constexpr int QV = RF_SUB / V;           // 16-byte vectors per staged row
+  const int tm = tid >> 5, tn = tid & 31;  // rows tm*4..+3, columns tn*4..+3 of the pass
+  for (int n0 = 0; n0 < N; n0 += RF_NT) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int fs = f0; fs < f0 + RF_CHUNK && fs < F; fs += RF_SUB) {
+      const bool vec_ok = (F % V == 0) && (fs + RF_SUB <= F);
+      __syncthreads();
+      if (vec_ok) {
+        for (int i = tid; i < RF_MT * QV; i += 256) {        // lane = row, warp-uniform vector index
+          const int r = i % RF_MT, q = i / RF_MT;
+          Vec16<T> v;
+          if (m0 + r < M) {
+            v.load(X + (size_t)(m0 + r) * F + fs + q * V);
+          } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) v.v[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) Xs[q * V + e][r] = v.v[e];
+        }
+        for (int i = tid; i < RF_NT * QV; i += 256) {
+          const int r = i % RF_NT, q = i / RF_NT;
+          Vec16<T> v;
+          if (n0 + r < N) {
+            v.load(Wm + (size_t)(n0 + r) * F + fs + q * V);
+          } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) v.v[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) Ws[q * V + e][r] = v.v[e];
+        }
+      } else {
+        for (int i = tid; i < RF_MT * RF_SUB; i += 256) {
+          const int r = i % RF_MT, f = i / RF_MT;
+          Xs[f][r] = (m0 + r < M && fs + f < F) ? Elem<T>::to_f(X[(size_t)(m0 + r) * F + fs + f]) : 0.f;
+        }
+        for (int i = tid; i < RF_NT * RF_SUB; i += 256) {
+          const int r = i % RF_NT, f = i / RF_NT;
+          Ws[f][r] = (n0 + r < N && fs + f < F) ? Elem<T>::to_f(Wm[(size_t)(n0 + r) * F + fs + f]) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int f = 0; f < RF_SUB; ++f) {
+        const float4 a = *reinterpret_cast<const float4*>(&Xs[f][tm * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Ws[f][tn * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + tm * 4 + i, n = n0 + tn * 4;
+      if (m >= M) continue;
+      float* o = part + ((size_t)chunk * M + m) * N + n;
+      if ((N & 3) == 0 && n + 3 < N) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       } else {
 #pragma unroll
-        for (int e = 0; e < V; ++e) v.v[e] = 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < V; ++e) Xs[r][q * V + e] = v.v[e];
-    }
-  } else
-  for (int i = tid; i < RF_MT * RF_CHUNK; i += 256) {
-    const int r = i / RF_CHUNK, f = i % RF_CHUNK;
-    float v = 0.f;
-    if (m0 + r < M && f0 + f < F) v = Elem<T>::to_f(X[(size_t)(m0 + r) * F + f0 + f]);
-    Xs[r][f] = v;
-  }
-  const int mr = tid >> 3, nq = tid & 7;  // row mr, columns nq + 8*j
-  for (int n0 = 0; n0 < N; n0 += RF_NT) {
-    __syncthreads();
-    if (vec_ok) {
-      for (int i = tid; i < RF_NT * (RF_CHUNK / V); i += 256) {
-        const int r = i / (RF_CHUNK / V), q = i % (RF_CHUNK / V);
-        Vec16<T> v;
-        if (n0 + r < N) {
-          v.load(Wm + (size_t)(n0 + r) * F + f0 + q * V);
-        } else {
-#pragma unroll
-          for (int e = 0; e < V; ++e) v.v[e] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < V; ++e) Ws[r][q * V + e] = v.v[e];
-      }
-    } else
-    for (int i = tid; i < RF_NT * RF_CHUNK; i += 256) {
-      const int r = i / RF_CHUNK, f = i % RF_CHUNK;
-      float v = 0.f;
-      if (n0 + r < N && f0 + f < F) v = Elem<T>::to_f(Wm[(size_t)(n0 + r) * F + f0 + f]);
-      Ws[r][f] = v;
-    }
-    __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int f = 0; f < RF_CHUNK; f += 4) {
-      const float4 xv = *reinterpret_cast<const float4*>(&Xs[mr][f]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 wv = *reinterpret_cast<const float4*>(&Ws[nq + 8 * j][f]);
-        acc[j] = fmaf(xv.x, wv.x, acc[j]);
-        acc[j] = fmaf(xv.y, wv.y, acc[j]);
-        acc[j] = fmaf(xv.z, wv.z, acc[j]);
-        acc[j] = fmaf(xv.w, wv.w, acc[j]);
-      }
-    }
-    if (m0 + mr < M) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + nq + 8 * j;
-        if (n < N) part[((size_t)chunk * M + m0 + mr) * N + n] = acc[j];
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) o[j] = acc[i][j];
       }
     }
   }
@@ -135,93 +144,103 @@ struct FcWide {
   int permC, permP;        // g(f) = (f % C)*P + f / C when permC > 0 else f
 };
 
-static constexpr int WF_MT = 32, WF_FT = 128, WF_KT = 16;
+static constexpr int WF_FT = 128, WF_KMAX = 128;
 
 // With the NHWC -> NCHW feature permutation (permC > 0: the weight-gradient outputs, reference layout [..][C*P]) a
 // CTA's 128 features are a (16 pixels x 8 channels) patch when P % 16 == 0 and C % 8 == 0: Bm is read as 16-byte
 // channel runs, and every thread stores four consecutive pixels of one channel -- 16 contiguous bytes -- instead of
 // four 4-byte stores P floats apart.  Otherwise the tile is 128 consecutive features.
-template <typename TB, typename TO>
-__global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
-  __shared__ __align__(16) float As[WF_KT][WF_MT + 4];
-  __shared__ __align__(16) float Bs[WF_KT][WF_FT + 4];
+//
+// The whole K extent (<= 128 per pass; K is L, 2L or the batch) of both operands is staged in shared memory in ONE
+// phase, every thread issuing all of its 16-byte loads before the barrier: the kernel is a stream over Bm, and a
+// K loop of small tiles with a barrier pair per tile exposed DRAM latency once per tile.  TM = rows per thread
+// (CTA tile = 8*TM rows x 128 features): 4 for M <= 32, 8 for the weight-gradient shapes so the Bm slab is re-read by
+// half as many CTAs.
+template <typename TB, typename TO, int TM>
+__global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p, int kt) {
+  constexpr int MT = 8 * TM;
+  constexpr int LDA = MT + 4, LDB = WF_FT + 4;
+  extern __shared__ __align__(16) float wf_sm[];
+  float* As = wf_sm;                        // [kt][LDA]
+  float* Bs = wf_sm + (size_t)kt * LDA;     // [kt][LDB]
   const TB* __restrict__ Bm = reinterpret_cast<const TB*>(p.Bm);
+  constexpr int VB = Vec16<TB>::N;
   const int tid = threadIdx.x;
   const bool patch = p.permC > 0 && p.permP % 16 == 0 && p.permC % 8 == 0;
-  const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * WF_MT;
-  const bool bvec = !patch && (p.F % Vec16<TB>::N == 0) && (f0 + WF_FT <= p.F);   // 16-byte loads of the B tile
+  const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * MT;
+  const bool bvec = !patch && (p.F % VB == 0) && (f0 + WF_FT <= p.F);   // 16-byte loads of the B tile
   int pc0 = 0, pp0 = 0;                       // patch origin (channel, pixel)
   if (patch) {
     const int ctiles = p.permC / 8;
     pc0 = (blockIdx.x % ctiles) * 8;
     pp0 = (blockIdx.x / ctiles) * 16;
   }
-  const int ty = tid >> 5, tx = tid & 31;  // rows ty*4..+3, tile-local features tx*4..+3
-  float acc[4][4];
+  const int ty = tid >> 5, tx = tid & 31;  // rows ty*TM..+TM-1, tile-local features tx*4..+3
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += WF_KT) {
-    __syncthreads();
-    for (int i = tid; i < WF_KT * WF_MT; i += 256) {
-      const int k = i / WF_MT, m = i % WF_MT;
+  for (int k0 = 0; k0 < p.K; k0 += kt) {
+    const int kn = min(kt, p.K - k0);
+    if (k0) __syncthreads();
+    for (int i = tid; i < kn * MT; i += 256) {
+      const int k = i / MT, m = i % MT;
       float v = 0.f;
-      if (k0 + k < p.K && m0 + m < p.M)
-        v = (m0 + m == p.ones_row) ? 1.f : p.A[(size_t)(m0 + m) * p.a_sm + (size_t)(k0 + k) * p.a_sk];
+      if (m0 + m < p.M) v = (m0 + m == p.ones_row) ? 1.f : p.A[(size_t)(m0 + m) * p.a_sm + (size_t)(k0 + k) * p.a_sk];
       if (p.a_clamp > 0.f && m0 + m != p.ones_row) v = fminf(fmaxf(v, -p.a_clamp), p.a_clamp);
-      As[k][m] = v;
+      As[k * LDA + m] = v;
     }
-    for (int i = tid; i < WF_KT * WF_FT; i += 256) {
-      const int k = i / WF_FT, fl = i % WF_FT;
-      float v = 0.f;
-      if (patch) {
-        // memory order: channel fastest (8-channel runs); tile-local order: pixel fastest within a channel
-        const int cl = fl & 7, pl = fl >> 3;
-        if (k0 + k < p.K) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + (size_t)(pp0 + pl) * p.permC + pc0 + cl]);
-        Bs[k][cl * 16 + pl] = v;
-      } else if (!bvec) {
-        if (k0 + k < p.K && f0 + fl < p.F) v = Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + f0 + fl]);
-        Bs[k][fl] = v;
+    if (patch) {
+      // memory order: channel fastest (8-channel runs, one or two 16-byte vectors); tile-local order: pixel fastest
+      constexpr int NV = 8 / VB;
+      for (int i = tid; i < kn * 16 * NV; i += 256) {
+        const int k = i / (16 * NV), r = i % (16 * NV), pl = r / NV, hv = r % NV;
+        Vec16<TB> v;
+        v.load(Bm + (size_t)(k0 + k) * p.F + (size_t)(pp0 + pl) * p.permC + pc0 + hv * VB);
+#pragma unroll
+        for (int e = 0; e < VB; ++e) Bs[k * LDB + (hv * VB + e) * 16 + pl] = v.v[e];
       }
-    }
-    if (!patch && bvec) {
-      constexpr int VB = Vec16<TB>::N;
-      for (int i = tid; i < WF_KT * (WF_FT / VB); i += 256) {
+    } else if (bvec) {
+      for (int i = tid; i < kn * (WF_FT / VB); i += 256) {
         const int k = i / (WF_FT / VB), q = i % (WF_FT / VB);
         Vec16<TB> v;
-        if (k0 + k < p.K) {
-          v.load(Bm + (size_t)(k0 + k) * p.F + f0 + q * VB);
-        } else {
+        v.load(Bm + (size_t)(k0 + k) * p.F + f0 + q * VB);
 #pragma unroll
-          for (int e = 0; e < VB; ++e) v.v[e] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < VB; ++e) Bs[k][q * VB + e] = v.v[e];
+        for (int e = 0; e < VB; ++e) Bs[k * LDB + q * VB + e] = v.v[e];
+      }
+    } else {
+      for (int i = tid; i < kn * WF_FT; i += 256) {
+        const int k = i / WF_FT, fl = i % WF_FT;
+        Bs[k * LDB + fl] = (f0 + fl < p.F) ? Elem<TB>::to_f(Bm[(size_t)(k0 + k) * p.F + f0 + fl]) : 0.f;
       }
     }
     __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kn; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k * LDB + tx * 4]);
+      const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < WF_KT; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      for (int h = 0; h < TM / 4; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k * LDA + ty * TM + h * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[h * 4 + i][j] = fmaf(av[i], bv[j], acc[h * 4 + i][j]);
+      }
     }
   }
   if (p.o0_sm == 1) {
-    // output is row-contiguous in m (fc_dec dW [F][L]): stage the tile in shared memory and let each warp write one
-    // feature's 32 rows as one 128-byte segment
-    __shared__ float Cs[WF_FT][WF_MT + 1];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Cs[tx * 4 + j][ty * 4 + i] = acc[i][j];
+    // output is row-contiguous in m (fc_dec dW [F][L]): stage the tile in shared memory (reusing the operand
+    // buffers) and let each warp write one feature's rows as contiguous segments
     __syncthreads();
-    const int m = m0 + tx;   // lane = row
+    float* Cs = wf_sm;   // [WF_FT][MT + 1]
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Cs[(tx * 4 + j) * (MT + 1) + ty * TM + i] = acc[i][j];
+    __syncthreads();
     for (int fl = ty; fl < WF_FT; fl += 8) {
       long long g;
       long long fsrc;        // NHWC feature index (bias lookup)
@@ -235,20 +254,23 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
         g = p.permC > 0 ? (long long)(f % p.permC) * p.permP + f / p.permC : f;
         fsrc = f;
       }
-      if (m >= p.M) continue;
-      const bool lo = m < p.split;
-      TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
-      const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
-      const long long mm = lo ? m : m - p.split;
-      float v = Cs[fl][tx];
-      if (p.bias) v += p.bias[fsrc];
-      base[mm * sm + g * sf] = Elem<TO>::from_f(v);
+      for (int ml = tx; ml < MT; ml += 32) {   // lane = row
+        const int m = m0 + ml;
+        if (m >= p.M) continue;
+        const bool lo = m < p.split;
+        TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
+        const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
+        const long long mm = lo ? m : m - p.split;
+        float v = Cs[fl * (MT + 1) + ml];
+        if (p.bias) v += p.bias[fsrc];
+        base[mm * sm + g * sf] = Elem<TO>::from_f(v);
+      }
     }
     return;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= p.M) continue;
     const bool lo = m < p.split;
     TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
@@ -269,6 +291,18 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
       }
       continue;
     }
+    if (bvec && sf == 1 && p.permC == 0 && sizeof(TO) == 2) {
+      // four consecutive features of one row: one 8-byte store
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + (p.bias ? p.bias[f0 + tx * 4 + j] : 0.f);
+      __nv_bfloat162 lo2 = __floats2bfloat162_rn(v[0], v[1]), hi2 = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + mm * sm + f0 + tx * 4) = pk;
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int f = f0 + tx * 4 + j;
@@ -283,8 +317,19 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p) {
 
 template <typename TB, typename TO>
 static int wide_f_launch(const FcWide& p, cudaStream_t st) {
-  dim3 grid(cdiv(p.F, WF_FT), cdiv(p.M, WF_MT));
-  fc_wide_f_kernel<TB, TO><<<grid, 256, 0, st>>>(p);
+  const int kt = p.K < WF_KMAX ? p.K : WF_KMAX;
+  const bool big = p.M > 32;
+  const int MT = big ? 64 : 32;
+  size_t smem = (size_t)kt * ((MT + 4) + (WF_FT + 4)) * sizeof(float);
+  const size_t cs = (size_t)WF_FT * (MT + 1) * sizeof(float);
+  if (p.o0_sm == 1 && cs > smem) smem = cs;
+  dim3 grid(cdiv(p.F, WF_FT), cdiv(p.M, MT));
+  auto kern = big ? fc_wide_f_kernel<TB, TO, 8> : fc_wide_f_kernel<TB, TO, 4>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WF_KMAX * (68 + 132) * sizeof(float)));
+    if (e != cudaSuccess) return cuda_fail(e, "fc_wide_f: cudaFuncSetAttribute");
+  }
+  kern<<<grid, 256, smem, st>>>(p, kt);
   BVAE_LAUNCH_CHECK("fc_wide_f");
   return BVAE_OK;
 }
