@@ -116,9 +116,99 @@ __global__ void __launch_bounds__(256) fc_reduce_f_kernel(const T* __restrict__ 
   }
 }
 
+// ---- bf16: the same product on the warp-level tensor-core path -----------------------------------------------
+// These GEMMs have M = batch (32) and stream their long operand exactly once, so they are bound by HBM, not by math;
+// what the CUDA-core kernel above cannot do is stay out of the way of the loads (16 FMA issue slots per 8 bytes of
+// W).  mma.sync m16n8k16 needs one issue slot per 4096 MACs, which leaves the kernel a single load phase: every
+// thread issues all of its 16-byte loads, one barrier, 32 MMAs per warp, store.  (tcgen05 would add a TMEM
+// allocation and an mbarrier pipeline around 16 KB of work per CTA; the tensor-pipe rate is irrelevant here.)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+static constexpr int RM_LD = RF_CHUNK + 8;   // bf16 elements per staged row (272 B: conflict-free fragment reads)
+
+// grid (F / 128, ceil(M / 32)); requires F % 128 == 0
+__global__ void __launch_bounds__(256) fc_reduce_f_mma_kernel(const __nv_bfloat16* __restrict__ X,
+                                                              const __nv_bfloat16* __restrict__ Wm,
+                                                              float* __restrict__ part, int M, int N, int F) {
+  __shared__ __align__(16) __nv_bfloat16 Xs[RF_MT][RM_LD];
+  __shared__ __align__(16) __nv_bfloat16 Ws[RF_NT][RM_LD];
+  const int chunk = blockIdx.x, m0 = blockIdx.y * RF_MT;
+  const size_t f0 = (size_t)chunk * RF_CHUNK;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int n0 = 0; n0 < N; n0 += RF_NT) {
+    if (n0) __syncthreads();
+    if (n0 == 0) {
+      for (int i = tid; i < RF_MT * (RF_CHUNK / 8); i += 256) {
+        const int r = i / (RF_CHUNK / 8), q = i % (RF_CHUNK / 8);
+        *reinterpret_cast<uint4*>(&Xs[r][q * 8]) =
+            (m0 + r < M) ? *reinterpret_cast<const uint4*>(X + (size_t)(m0 + r) * F + f0 + q * 8) : zero;
+      }
+    }
+    for (int i = tid; i < RF_NT * (RF_CHUNK / 8); i += 256) {
+      const int r = i / (RF_CHUNK / 8), q = i % (RF_CHUNK / 8);
+      *reinterpret_cast<uint4*>(&Ws[r][q * 8]) =
+          (n0 + r < N) ? *reinterpret_cast<const uint4*>(Wm + (size_t)(n0 + r) * F + f0 + q * 8) : zero;
+    }
+    __syncthreads();
+    const int nw = warp * 16;                 // this warp's 16 output columns of the pass
+    if (n0 + nw >= N) continue;
+    float acc[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < RF_CHUNK; k0 += 16) {
+      uint32_t a[2][4], b[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        a[i][0] = *reinterpret_cast<const uint32_t*>(&Xs[i * 16 + g][k0 + 2 * t]);
+        a[i][1] = *reinterpret_cast<const uint32_t*>(&Xs[i * 16 + g + 8][k0 + 2 * t]);
+        a[i][2] = *reinterpret_cast<const uint32_t*>(&Xs[i * 16 + g][k0 + 2 * t + 8]);
+        a[i][3] = *reinterpret_cast<const uint32_t*>(&Xs[i * 16 + g + 8][k0 + 2 * t + 8]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        b[j][0] = *reinterpret_cast<const uint32_t*>(&Ws[nw + j * 8 + g][k0 + 2 * t]);
+        b[j][1] = *reinterpret_cast<const uint32_t*>(&Ws[nw + j * 8 + g][k0 + 2 * t + 8]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma_bf16_16816(acc[i][j], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int m = m0 + i * 16 + g + hrow * 8, n = n0 + nw + j * 8 + 2 * t;
+          if (m >= M) continue;
+          float* o = part + ((size_t)chunk * M + m) * N + n;
+          if (n < N) o[0] = acc[i][j][hrow * 2];
+          if (n + 1 < N) o[1] = acc[i][j][hrow * 2 + 1];
+        }
+  }
+}
+
 template <typename T>
 static int reduce_f_launch(const void* X, const void* Wm, float* part, int M, int N, int F, cudaStream_t st) {
   dim3 grid(cdiv(F, RF_CHUNK), cdiv(M, RF_MT));
+  if (sizeof(T) == 2 && F % RF_CHUNK == 0) {
+    fc_reduce_f_mma_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wm, part, M, N, F);
+    BVAE_LAUNCH_CHECK("fc_reduce_f_mma");
+    return BVAE_OK;
+  }
   fc_reduce_f_kernel<T><<<grid, 256, 0, st>>>((const T*)X, (const T*)Wm, part, M, N, F);
   BVAE_LAUNCH_CHECK("fc_reduce_f");
   return BVAE_OK;
@@ -315,8 +405,209 @@ __global__ void __launch_bounds__(256) fc_wide_f_kernel(const FcWide p, int kt) 
   }
 }
 
+// ---- bf16: wide-F on the warp-level tensor-core path (see fc_reduce_f_mma_kernel for why mma.sync) ------------
+// CTA = 128 features x all M rows (<= 16 * MTILES); warp w owns features [16w, 16w + 16).  Bm is staged as
+// [k][feature] and read through ldmatrix.trans (the contraction index is its slow dimension); the small fp32
+// operand A (gradients / latents) is split into bf16 hi + lo parts, two MMAs per tile, so the product keeps fp32-level
+// accuracy in A while Bm -- already bf16 in memory -- is used as is.
+static constexpr int WM_LDB = WF_FT + 8;   // bf16 elements per staged Bm row
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <typename TO>
+__device__ __forceinline__ void wm_store2(TO* dst, float a, float b);
+template <>
+__device__ __forceinline__ void wm_store2<float>(float* dst, float a, float b) {
+  *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+}
+template <>
+__device__ __forceinline__ void wm_store2<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
+}
+
+// kt = K rounded up to 16, at most 128 per pass.  Requires F % 8 == 0 and every tile inside F (F % 128 == 0).
+template <typename TO, int MTILES>
+__global__ void __launch_bounds__(256) fc_wide_f_mma_kernel(const FcWide p, int kt) {
+  extern __shared__ __align__(16) uint8_t wm_raw[];
+  constexpr int MR = 16 * MTILES;
+  const int lda = kt + 8;
+  __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(wm_raw);   // [kt][WM_LDB]
+  __nv_bfloat16* Ahi = Bs + (size_t)kt * WM_LDB;                  // [MR][lda]
+  __nv_bfloat16* Alo = Ahi + (size_t)MR * lda;
+  const __nv_bfloat16* __restrict__ Bm = reinterpret_cast<const __nv_bfloat16*>(p.Bm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const bool patch = p.permC > 0 && p.permP % 16 == 0 && p.permC % 8 == 0;
+  const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * MR;
+  int pc0 = 0, pp0 = 0;
+  if (patch) {
+    const int ctiles = p.permC / 8;
+    pc0 = (blockIdx.x % ctiles) * 8;
+    pp0 = (blockIdx.x / ctiles) * 16;
+  }
+  float acc[MTILES][2][4];
+#pragma unroll
+  for (int i = 0; i < MTILES; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  const int mt_live = min(MTILES, (p.M - m0 + 15) / 16);
+  for (int k0 = 0; k0 < p.K; k0 += kt) {
+    const int kn = min(kt, p.K - k0);     // live rows of this pass; rows kn..kt-1 are zero
+    if (k0) __syncthreads();
+    // Every staging loop issues a batch of eight independent loads before it touches shared memory: with one load per
+    // iteration each trip paid a full L2 / DRAM round trip and the CTA spent most of its life waiting.
+    // Bm -> [k][tile-local feature]; patch order: pixel fastest within a channel.  (k, pl) / (k, q) = i / 16, i % 16.
+    for (int base = 0; base < kt * 16; base += 256 * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid, k = i >> 4, r = i & 15;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < kt * 16 && k < kn)
+          v[u] = patch ? *reinterpret_cast<const uint4*>(Bm + (size_t)(k0 + k) * p.F + (size_t)(pp0 + r) * p.permC + pc0)
+                       : *reinterpret_cast<const uint4*>(Bm + (size_t)(k0 + k) * p.F + f0 + r * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid, k = i >> 4, r = i & 15;
+        if (i >= kt * 16) break;
+        if (patch) {
+          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v[u]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) Bs[k * WM_LDB + c * 16 + r] = e[c];
+        } else {
+          *reinterpret_cast<uint4*>(&Bs[k * WM_LDB + r * 8]) = v[u];
+        }
+      }
+    }
+    // A -> bf16 hi / lo, [m][k]
+    for (int base = 0; base < MR * kt; base += 256 * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        int k, m;
+        if (p.a_sk == 1) { k = i % kt; m = i / kt; } else { m = i % MR; k = i / MR; }
+        v[u] = 0.f;
+        if (i < MR * kt && k < kn && m0 + m < p.M && m0 + m != p.ones_row)
+          v[u] = p.A[(size_t)(m0 + m) * p.a_sm + (size_t)(k0 + k) * p.a_sk];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * 256 + tid;
+        if (i >= MR * kt) break;
+        int k, m;
+        if (p.a_sk == 1) { k = i % kt; m = i / kt; } else { m = i % MR; k = i / MR; }
+        float x = v[u];
+        if (p.a_clamp > 0.f) x = fminf(fmaxf(x, -p.a_clamp), p.a_clamp);
+        if (m0 + m == p.ones_row && k < kn) x = 1.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        Ahi[m * lda + k] = hi;
+        Alo[m * lda + k] = __float2bfloat16_rn(x - __bfloat162float(hi));
+      }
+    }
+    __syncthreads();
+    const int nw = warp * 16;
+    for (int kk = 0; kk < kt; kk += 16) {
+      uint32_t b[4];   // {n-tile 0: k lo, k hi; n-tile 1: k lo, k hi}
+      ldmatrix_x4_trans(b, &Bs[(kk + ((lane >> 3) & 1) * 8 + (lane & 7)) * WM_LDB + nw + (lane >> 4) * 8]);
+      const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+#pragma unroll
+      for (int i = 0; i < MTILES; ++i) {
+        if (i >= mt_live) break;
+        uint32_t ah[4], al[4];
+        const int r0 = (i * 16 + g) * lda + kk + 2 * t, r1 = r0 + 8 * lda;
+        ah[0] = *reinterpret_cast<const uint32_t*>(&Ahi[r0]);
+        ah[1] = *reinterpret_cast<const uint32_t*>(&Ahi[r1]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&Ahi[r0 + 8]);
+        ah[3] = *reinterpret_cast<const uint32_t*>(&Ahi[r1 + 8]);
+        al[0] = *reinterpret_cast<const uint32_t*>(&Alo[r0]);
+        al[1] = *reinterpret_cast<const uint32_t*>(&Alo[r1]);
+        al[2] = *reinterpret_cast<const uint32_t*>(&Alo[r0 + 8]);
+        al[3] = *reinterpret_cast<const uint32_t*>(&Alo[r1 + 8]);
+        mma_bf16_16816(acc[i][0], ah, b0);
+        mma_bf16_16816(acc[i][0], al, b0);
+        mma_bf16_16816(acc[i][1], ah, b1);
+        mma_bf16_16816(acc[i][1], al, b1);
+      }
+    }
+  }
+  // epilogue: thread holds (m = 16i + g [+8], tile-local features nw + 8j + 2t, +1)
+  const int nw = warp * 16;
+#pragma unroll
+  for (int i = 0; i < MTILES; ++i) {
+    if (i >= mt_live) break;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int fl = nw + j * 8 + 2 * t;
+      long long g0, fsrc0, fsrc1;
+      if (patch) {
+        const int c = pc0 + (fl >> 4), px = pp0 + (fl & 15);
+        g0 = (long long)c * p.permP + px;            // the next local feature is the next pixel of the same channel
+        fsrc0 = (long long)px * p.permC + c;
+        fsrc1 = fsrc0 + p.permC;
+      } else {
+        g0 = f0 + fl;
+        fsrc0 = g0;
+        fsrc1 = g0 + 1;
+      }
+      const float bias0 = p.bias ? p.bias[fsrc0] : 0.f, bias1 = p.bias ? p.bias[fsrc1] : 0.f;
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int m = m0 + i * 16 + g + hrow * 8;
+        if (m >= p.M) continue;
+        const bool lo = m < p.split;
+        TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
+        const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
+        const long long mm = lo ? m : m - p.split;
+        const float v0 = acc[i][j][hrow * 2] + bias0, v1 = acc[i][j][hrow * 2 + 1] + bias1;
+        if (patch || p.permC == 0) {
+          // two consecutive output positions g0, g0 + 1
+          if (sf == 1 && ((mm * sm) & 1) == 0) {
+            wm_store2<TO>(base + mm * sm + g0, v0, v1);
+          } else {
+            base[mm * sm + g0 * sf] = Elem<TO>::from_f(v0);
+            base[mm * sm + (g0 + 1) * sf] = Elem<TO>::from_f(v1);
+          }
+        } else {   // permuted without the patch mapping: generic scatter
+          const long long f = g0;
+          base[mm * sm + ((f % p.permC) * p.permP + f / p.permC) * sf] = Elem<TO>::from_f(v0);
+          base[mm * sm + (((f + 1) % p.permC) * p.permP + (f + 1) / p.permC) * sf] = Elem<TO>::from_f(v1);
+        }
+      }
+    }
+  }
+}
+
+template <typename TO>
+static int wide_f_mma_launch(const FcWide& p, cudaStream_t st) {
+  int kt = (p.K + 15) / 16 * 16;
+  if (kt > WF_KMAX) kt = WF_KMAX;
+  const bool small = p.M <= 32;
+  const int MR = small ? 32 : 128;
+  const size_t smem = ((size_t)kt * WM_LDB + 2 * (size_t)MR * (kt + 8)) * sizeof(__nv_bfloat16);
+  auto kern = small ? fc_wide_f_mma_kernel<TO, 2> : fc_wide_f_mma_kernel<TO, 8>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "fc_wide_f_mma: cudaFuncSetAttribute");
+  }
+  dim3 grid(p.F / WF_FT, cdiv(p.M, MR));
+  kern<<<grid, 256, smem, st>>>(p, kt);
+  BVAE_LAUNCH_CHECK("fc_wide_f_mma");
+  return BVAE_OK;
+}
+
 template <typename TB, typename TO>
 static int wide_f_launch(const FcWide& p, cudaStream_t st) {
+  if (sizeof(TB) == 2 && p.F % WF_FT == 0) return wide_f_mma_launch<TO>(p, st);
+
   const int kt = p.K < WF_KMAX ? p.K : WF_KMAX;
   const bool big = p.M > 32;
   const int MT = big ? 64 : 32;
