@@ -430,34 +430,62 @@ __device__ __forceinline__ void wm_store2<__nv_bfloat16>(__nv_bfloat16* dst, flo
   *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
 }
 
-// kt = K rounded up to 16, at most 128 per pass.  Requires F % 8 == 0 and every tile inside F (F % 128 == 0).
-template <typename TO, int MTILES>
-__global__ void __launch_bounds__(256) fc_wide_f_mma_kernel(const FcWide p, int kt) {
+// generic permuted scatter (permC > 0 without the patch mapping): rare, kept out of line so the hot epilogue stays small
+template <typename TO>
+__device__ __noinline__ void wm_scatter2(TO* rowp, long long sf, long long f, int C, int P, float v0, float v1) {
+  rowp[((f % C) * P + f / C) * sf] = Elem<TO>::from_f(v0);
+  rowp[(((f + 1) % C) * P + (f + 1) / C) * sf] = Elem<TO>::from_f(v1);
+}
+
+// kt = 1 << ktlog = K rounded up to a power of two in [16, 128] (rows beyond K are zero), at most 128 per pass; a
+// CTA stages up to 128 rows of A and walks them in blocks of 32 (two m16 tiles).  Requires every tile inside F
+// (F % 128 == 0).  The code is deliberately compact -- shift/mask indexing, precomputed row pointers, a real loop over
+// the row blocks: every warp runs it once, and a fully unrolled 8-tile version spent 53 % of its issue slots waiting
+// for instruction fetch (ncu: stall "no_instructions").  Passes after the first (K > 128: the batch of a weight
+// gradient) add into the fp32 output, same thread, same order: deterministic.
+template <typename TO>
+__global__ void __launch_bounds__(256) fc_wide_f_mma_kernel(const FcWide p, int ktlog, int mrlog) {
+  const int kt = 1 << ktlog, mr = 1 << mrlog;   // rows staged per CTA: 32, 64 or 128
   extern __shared__ __align__(16) uint8_t wm_raw[];
-  constexpr int MR = 16 * MTILES;
   const int lda = kt + 8;
   __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(wm_raw);   // [kt][WM_LDB]
-  __nv_bfloat16* Ahi = Bs + (size_t)kt * WM_LDB;                  // [MR][lda]
-  __nv_bfloat16* Alo = Ahi + (size_t)MR * lda;
+  __nv_bfloat16* Ahi = Bs + (size_t)kt * WM_LDB;                  // [mr][lda]
+  __nv_bfloat16* Alo = Ahi + (size_t)mr * lda;
   const __nv_bfloat16* __restrict__ Bm = reinterpret_cast<const __nv_bfloat16*>(p.Bm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const bool patch = p.permC > 0 && p.permP % 16 == 0 && p.permC % 8 == 0;
-  const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * MR;
+  const int f0 = blockIdx.x * WF_FT, m0 = blockIdx.y * mr;
   int pc0 = 0, pp0 = 0;
   if (patch) {
     const int ctiles = p.permC / 8;
     pc0 = (blockIdx.x % ctiles) * 8;
     pp0 = (blockIdx.x / ctiles) * 16;
   }
-  float acc[MTILES][2][4];
+  // output columns of this thread: tile-local features nw + 8j + 2t, +1
+  const int nw = warp * 16;
+  const bool pair = patch || p.permC == 0;   // the two features of a fragment pair are adjacent in the output
+  long long goff[2];
+  float bias0[2], bias1[2];
 #pragma unroll
-  for (int i = 0; i < MTILES; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
-  const int mt_live = min(MTILES, (p.M - m0 + 15) / 16);
+  for (int j = 0; j < 2; ++j) {
+    const int fl = nw + j * 8 + 2 * t;
+    long long fsrc0, fsrc1;
+    if (patch) {
+      const int c = pc0 + (fl >> 4), px = pp0 + (fl & 15);
+      goff[j] = (long long)c * p.permP + px;       // the next local feature is the next pixel of the same channel
+      fsrc0 = (long long)px * p.permC + c;
+      fsrc1 = fsrc0 + p.permC;
+    } else {
+      goff[j] = f0 + fl;
+      fsrc0 = goff[j];
+      fsrc1 = fsrc0 + 1;
+    }
+    bias0[j] = p.bias ? p.bias[fsrc0] : 0.f;
+    bias1[j] = p.bias ? p.bias[fsrc1] : 0.f;
+  }
+  const int rows = min(mr, p.M - m0);
+  const bool kfast = p.a_sk == 1;
   for (int k0 = 0; k0 < p.K; k0 += kt) {
     const int kn = min(kt, p.K - k0);     // live rows of this pass; rows kn..kt-1 are zero
     if (k0) __syncthreads();
@@ -488,23 +516,21 @@ __global__ void __launch_bounds__(256) fc_wide_f_mma_kernel(const FcWide p, int 
       }
     }
     // A -> bf16 hi / lo, [m][k]
-    for (int base = 0; base < MR * kt; base += 256 * 8) {
+    for (int base = 0; base < mr * kt; base += 256 * 8) {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = base + u * 256 + tid;
-        int k, m;
-        if (p.a_sk == 1) { k = i % kt; m = i / kt; } else { m = i % MR; k = i / MR; }
+        const int k = kfast ? (i & (kt - 1)) : (i >> mrlog), m = kfast ? (i >> ktlog) : (i & (mr - 1));
         v[u] = 0.f;
-        if (i < MR * kt && k < kn && m0 + m < p.M && m0 + m != p.ones_row)
+        if (i < mr * kt && k < kn && m < rows && m0 + m != p.ones_row)
           v[u] = p.A[(size_t)(m0 + m) * p.a_sm + (size_t)(k0 + k) * p.a_sk];
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = base + u * 256 + tid;
-        if (i >= MR * kt) break;
-        int k, m;
-        if (p.a_sk == 1) { k = i % kt; m = i / kt; } else { m = i % MR; k = i / MR; }
+        if (i >= mr * kt) break;
+        const int k = kfast ? (i & (kt - 1)) : (i >> mrlog), m = kfast ? (i >> ktlog) : (i & (mr - 1));
         float x = v[u];
         if (p.a_clamp > 0.f) x = fminf(fmaxf(x, -p.a_clamp), p.a_clamp);
         if (m0 + m == p.ones_row && k < kn) x = 1.f;
@@ -514,99 +540,107 @@ __global__ void __launch_bounds__(256) fc_wide_f_mma_kernel(const FcWide p, int 
       }
     }
     __syncthreads();
-    const int nw = warp * 16;
-    for (int kk = 0; kk < kt; kk += 16) {
-      uint32_t b[4];   // {n-tile 0: k lo, k hi; n-tile 1: k lo, k hi}
-      ldmatrix_x4_trans(b, &Bs[(kk + ((lane >> 3) & 1) * 8 + (lane & 7)) * WM_LDB + nw + (lane >> 4) * 8]);
-      const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+#pragma unroll 1
+    for (int mb = 0; mb < rows; mb += 32) {
+      float acc[2][2][4];
 #pragma unroll
-      for (int i = 0; i < MTILES; ++i) {
-        if (i >= mt_live) break;
-        uint32_t ah[4], al[4];
-        const int r0 = (i * 16 + g) * lda + kk + 2 * t, r1 = r0 + 8 * lda;
-        ah[0] = *reinterpret_cast<const uint32_t*>(&Ahi[r0]);
-        ah[1] = *reinterpret_cast<const uint32_t*>(&Ahi[r1]);
-        ah[2] = *reinterpret_cast<const uint32_t*>(&Ahi[r0 + 8]);
-        ah[3] = *reinterpret_cast<const uint32_t*>(&Ahi[r1 + 8]);
-        al[0] = *reinterpret_cast<const uint32_t*>(&Alo[r0]);
-        al[1] = *reinterpret_cast<const uint32_t*>(&Alo[r1]);
-        al[2] = *reinterpret_cast<const uint32_t*>(&Alo[r0 + 8]);
-        al[3] = *reinterpret_cast<const uint32_t*>(&Alo[r1 + 8]);
-        mma_bf16_16816(acc[i][0], ah, b0);
-        mma_bf16_16816(acc[i][0], al, b0);
-        mma_bf16_16816(acc[i][1], ah, b1);
-        mma_bf16_16816(acc[i][1], al, b1);
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+#pragma unroll 1
+      for (int kk = 0; kk < kt; kk += 16) {
+        uint32_t b[4];   // {n-tile 0: k lo, k hi; n-tile 1: k lo, k hi}
+        ldmatrix_x4_trans(b, &Bs[(kk + ((lane >> 3) & 1) * 8 + (lane & 7)) * WM_LDB + nw + (lane >> 4) * 8]);
+        const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint32_t ah[4], al[4];
+          const int r0 = (mb + i * 16 + g) * lda + kk + 2 * t, r1 = r0 + 8 * lda;
+          ah[0] = *reinterpret_cast<const uint32_t*>(&Ahi[r0]);
+          ah[1] = *reinterpret_cast<const uint32_t*>(&Ahi[r1]);
+          ah[2] = *reinterpret_cast<const uint32_t*>(&Ahi[r0 + 8]);
+          ah[3] = *reinterpret_cast<const uint32_t*>(&Ahi[r1 + 8]);
+          al[0] = *reinterpret_cast<const uint32_t*>(&Alo[r0]);
+          al[1] = *reinterpret_cast<const uint32_t*>(&Alo[r1]);
+          al[2] = *reinterpret_cast<const uint32_t*>(&Alo[r0 + 8]);
+          al[3] = *reinterpret_cast<const uint32_t*>(&Alo[r1 + 8]);
+          mma_bf16_16816(acc[i][0], ah, b0);
+          mma_bf16_16816(acc[i][0], al, b0);
+          mma_bf16_16816(acc[i][1], ah, b1);
+          mma_bf16_16816(acc[i][1], al, b1);
+        }
       }
-    }
-  }
-  // epilogue: thread holds (m = 16i + g [+8], tile-local features nw + 8j + 2t, +1)
-  const int nw = warp * 16;
+      // rows mb + 16i + g (+8); thread holds two adjacent features per (i, j, half)
 #pragma unroll
-  for (int i = 0; i < MTILES; ++i) {
-    if (i >= mt_live) break;
+      for (int i = 0; i < 2; ++i) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int fl = nw + j * 8 + 2 * t;
-      long long g0, fsrc0, fsrc1;
-      if (patch) {
-        const int c = pc0 + (fl >> 4), px = pp0 + (fl & 15);
-        g0 = (long long)c * p.permP + px;            // the next local feature is the next pixel of the same channel
-        fsrc0 = (long long)px * p.permC + c;
-        fsrc1 = fsrc0 + p.permC;
-      } else {
-        g0 = f0 + fl;
-        fsrc0 = g0;
-        fsrc1 = g0 + 1;
-      }
-      const float bias0 = p.bias ? p.bias[fsrc0] : 0.f, bias1 = p.bias ? p.bias[fsrc1] : 0.f;
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int m = m0 + mb + i * 16 + g + hrow * 8;
+          if (m >= p.M) continue;
+          const bool lo = m < p.split;
+          TO* rowp = lo ? reinterpret_cast<TO*>(p.out0) + (long long)m * p.o0_sm
+                        : reinterpret_cast<TO*>(p.out1) + (long long)(m - p.split) * p.o1_sm;
+          const long long sf = lo ? p.o0_sf : p.o1_sf;
+          const bool vec = pair && sf == 1 && (reinterpret_cast<uintptr_t>(rowp) & (2 * sizeof(TO) - 1)) == 0;
 #pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow) {
-        const int m = m0 + i * 16 + g + hrow * 8;
-        if (m >= p.M) continue;
-        const bool lo = m < p.split;
-        TO* base = reinterpret_cast<TO*>(lo ? p.out0 : p.out1);
-        const long long sm = lo ? p.o0_sm : p.o1_sm, sf = lo ? p.o0_sf : p.o1_sf;
-        const long long mm = lo ? m : m - p.split;
-        const float v0 = acc[i][j][hrow * 2] + bias0, v1 = acc[i][j][hrow * 2 + 1] + bias1;
-        if (patch || p.permC == 0) {
-          // two consecutive output positions g0, g0 + 1
-          if (sf == 1 && ((mm * sm) & 1) == 0) {
-            wm_store2<TO>(base + mm * sm + g0, v0, v1);
-          } else {
-            base[mm * sm + g0 * sf] = Elem<TO>::from_f(v0);
-            base[mm * sm + (g0 + 1) * sf] = Elem<TO>::from_f(v1);
+          for (int j = 0; j < 2; ++j) {
+            float v0 = acc[i][j][hrow * 2], v1 = acc[i][j][hrow * 2 + 1];
+            if (k0 == 0) {
+              v0 += bias0[j];
+              v1 += bias1[j];
+            } else if (pair) {   // later K passes add into the (fp32) output
+              v0 += Elem<TO>::to_f(rowp[goff[j] * sf]);
+              v1 += Elem<TO>::to_f(rowp[(goff[j] + 1) * sf]);
+            }
+            if (vec) {
+              wm_store2<TO>(rowp + goff[j], v0, v1);     // goff is even: aligned pair
+            } else if (pair) {
+              rowp[goff[j] * sf] = Elem<TO>::from_f(v0);
+              rowp[(goff[j] + 1) * sf] = Elem<TO>::from_f(v1);
+            } else {
+              wm_scatter2<TO>(rowp, sf, goff[j], p.permC, p.permP, v0, v1);
+            }
           }
-        } else {   // permuted without the patch mapping: generic scatter
-          const long long f = g0;
-          base[mm * sm + ((f % p.permC) * p.permP + f / p.permC) * sf] = Elem<TO>::from_f(v0);
-          base[mm * sm + (((f + 1) % p.permC) * p.permP + (f + 1) / p.permC) * sf] = Elem<TO>::from_f(v1);
         }
       }
     }
   }
 }
 
+// bf16 Bm, every tile inside F, and either a single K pass or an fp32 output that later passes can add into
+template <typename TO>
+static bool wide_f_mma_ok(const FcWide& p) {
+  if (p.F % WF_FT) return false;
+  if (p.K <= WF_KMAX) return true;
+  const bool pair = p.permC == 0 || (p.permP % 16 == 0 && p.permC % 8 == 0);
+  return sizeof(TO) == 4 && pair;
+}
+
 template <typename TO>
 static int wide_f_mma_launch(const FcWide& p, cudaStream_t st) {
-  int kt = (p.K + 15) / 16 * 16;
-  if (kt > WF_KMAX) kt = WF_KMAX;
-  const bool small = p.M <= 32;
-  const int MR = small ? 32 : 128;
-  const size_t smem = ((size_t)kt * WM_LDB + 2 * (size_t)MR * (kt + 8)) * sizeof(__nv_bfloat16);
-  auto kern = small ? fc_wide_f_mma_kernel<TO, 2> : fc_wide_f_mma_kernel<TO, 8>;
+  int ktlog = 4;
+  while ((1 << ktlog) < p.K && (1 << ktlog) < WF_KMAX) ++ktlog;
+  const int kt = 1 << ktlog;
+  int mrlog = 5;
+  while ((1 << mrlog) < p.M && mrlog < 7) ++mrlog;
+  const int mr = 1 << mrlog;
+  const size_t smem = ((size_t)kt * WM_LDB + 2 * (size_t)mr * (kt + 8)) * sizeof(__nv_bfloat16);
+  auto kern = fc_wide_f_mma_kernel<TO>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "fc_wide_f_mma: cudaFuncSetAttribute");
   }
-  dim3 grid(p.F / WF_FT, cdiv(p.M, MR));
-  kern<<<grid, 256, smem, st>>>(p, kt);
+  dim3 grid(p.F / WF_FT, cdiv(p.M, mr));
+  kern<<<grid, 256, smem, st>>>(p, ktlog, mrlog);
   BVAE_LAUNCH_CHECK("fc_wide_f_mma");
   return BVAE_OK;
 }
 
 template <typename TB, typename TO>
 static int wide_f_launch(const FcWide& p, cudaStream_t st) {
-  if (sizeof(TB) == 2 && p.F % WF_FT == 0) return wide_f_mma_launch<TO>(p, st);
+  if (sizeof(TB) == 2 && wide_f_mma_ok<TO>(p)) return wide_f_mma_launch<TO>(p, st);
 
   const int kt = p.K < WF_KMAX ? p.K : WF_KMAX;
   const bool big = p.M > 32;
