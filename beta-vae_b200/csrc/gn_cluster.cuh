@@ -10,7 +10,7 @@ int gn_cluster_fwd(const T* y, T* out, const float* gamma, const float* beta, co
                    const float* w2, const float* b2, int B, int P, int C, int R, float* stats, float* cpos, float* spos,
                    float* hidden, float* gate, cudaStream_t st, bool* handled);
 
-// Writes dy and the per-sample G1, G2 (and dz2, dz1 with SE) that gn_bwd_params_kernel sums over the batch.
+// Writes dy and the per-sample G1, G2 (and dz2, dz1 with SE) that the gn_bwd_params_* kernels (gn_se.cu) sum over the batch.
 template <typename T>
 int gn_cluster_bwd(const T* dout, const T* y, T* dy, const float* gamma, const float* beta, const float* w1,
                    const float* w2, int B, int P, int C, int R, const float* stats, const float* cpos, const float* spos,

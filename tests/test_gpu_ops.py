@@ -186,7 +186,9 @@ def _gn_se_ref(y, gamma, beta, se):
                                    (2, 64, 64, 8, 0), (4, 8, 8, 512, 64), (2, 8, 8, 16, 0),
                                    # cluster-resident kernels (gn_se_cluster.cu): 8- and 16-CTA clusters, split SE mat-vecs
                                    (2, 64, 64, 64, 8), (2, 128, 128, 64, 8), (3, 32, 32, 128, 16), (2, 16, 16, 256, 32),
-                                   (2, 128, 128, 16, 0), (40, 16, 16, 64, 8)])
+                                   (2, 128, 128, 16, 0), (40, 16, 16, 64, 8),
+                                   # tiled SE weight-gradient kernel: channel tail (72 = 2 * 32 + 8), batch tail (37 = 32 + 5)
+                                   (3, 4, 4, 72, 40), (37, 4, 4, 128, 32)])
 def test_gn_relu_se(shape, prec):
     ops = _ops()
     dtype, tol = DT[prec]
