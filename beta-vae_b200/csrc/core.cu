@@ -203,13 +203,22 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   float acc = 0.f;
   const size_t n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = g4[i];
-    acc = fmaf(v.x, v.x, acc);
-    acc = fmaf(v.y, v.y, acc);
-    acc = fmaf(v.z, v.z, acc);
-    acc = fmaf(v.w, v.w, acc);
+  // four independent 16-byte loads and accumulator chains per trip
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < n4) ? g4[i + u * stride] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a4[u] = fmaf(v[u].x, v[u].x, a4[u]);
+      a4[u] = fmaf(v[u].y, v[u].y, a4[u]);
+      a4[u] = fmaf(v[u].z, v[u].z, a4[u]);
+      a4[u] = fmaf(v[u].w, v[u].w, a4[u]);
+    }
   }
+  acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   if (blockIdx.x == 0)
     for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) acc = fmaf(g[i], g[i], acc);
   const double s = block_sum((double)acc, red);

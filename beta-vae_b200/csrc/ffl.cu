@@ -21,15 +21,15 @@ __device__ __forceinline__ float ffl_mult(int j, int W) { return (j == 0 || (2 *
 __global__ void __launch_bounds__(256)
     ffl_power_kernel(const float2* __restrict__ z, double* __restrict__ part, int B, int C, int H, int Wh, int W) {
   __shared__ double red[32];
-  const long long per = (long long)H * Wh;
+  // the grid strides over ALL B * H * Wh elements of a channel (a per-sample inner loop left most CTAs idle and the
+  // rest walking the batch one dependent load at a time)
+  const long long per = (long long)H * Wh, n = (long long)B * per;
   for (int c = 0; c < C; ++c) {
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float2* src = z + ((long long)b * C + c) * per;
-      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-        const float2 v = src[i];
-        acc = fmaf(ffl_mult((int)(i % Wh), W), fmaf(v.x, v.x, v.y * v.y), acc);
-      }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const long long b = i / per, r = i - b * per;
+      const float2 v = z[(b * C + c) * per + r];
+      acc = fmaf(ffl_mult((int)(r % Wh), W), fmaf(v.x, v.x, v.y * v.y), acc);
     }
     const double s = block_sum((double)acc, red);
     if (threadIdx.x == 0) part[(size_t)c * gridDim.x + blockIdx.x] = s;
@@ -50,18 +50,17 @@ __global__ void __launch_bounds__(256)
     const float s = (float)(t / N) + eps;
     if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[c] = s;
     float acc = 0.f, accu = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float2* src = z + ((long long)b * C + c) * per;
-      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-        const float2 v = src[i];
-        const float p = fmaf(v.x, v.x, v.y * v.y);
-        const float r = p / s;
-        const bool clamped = r < eps;
-        const float w = alpha == 1.f ? fmaxf(r, eps) : powf(fmaxf(r, eps), alpha);
-        const float term = ffl_mult((int)(i % Wh), W) * w * p;
-        acc += term;
-        accu += clamped ? 0.f : term;
-      }
+    const long long n = (long long)B * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const long long b = i / per, q = i - b * per;
+      const float2 v = z[(b * C + c) * per + q];
+      const float p = fmaf(v.x, v.x, v.y * v.y);
+      const float r = p / s;
+      const bool clamped = r < eps;
+      const float w = alpha == 1.f ? fmaxf(r, eps) : powf(fmaxf(r, eps), alpha);
+      const float term = ffl_mult((int)(q % Wh), W) * w * p;
+      acc += term;
+      accu += clamped ? 0.f : term;
     }
     const double a = block_sum((double)acc, red);
     const double u = block_sum((double)accu, red);

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 }
 
 // D[p][t] = dlogit[p - off_t] for t < 9 (zero outside the image), 0 for t >= 9; bpart[cta] = sum of dlogit (bias grad)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
     final_im2col16_kernel(const float* __restrict__ dlogit, __nv_bfloat16* __restrict__ dcol, float* __restrict__ bpart,
                           int B, int H, int W) {
   __shared__ float red[32];
@@ -368,7 +368,8 @@ int finalconv_bwd_tc(const void* h, const float* w, const float* dlogit, void* d
   const int sms = num_sms();
   const int tiles = (W / 8) * (H / 16) * B;
   const int grid = tiles < sms ? tiles : sms;
-  final_im2col16_kernel<<<grid, 256, 0, st>>>(dlogit, dcol, bpart, B, H, W);   // same CTA count as the main kernel
+  // same CTA count as the main kernel (one bias partial per CTA); 1024 threads each so that a thread walks ~4 pixels
+  final_im2col16_kernel<<<grid, 1024, 0, st>>>(dlogit, dcol, bpart, B, H, W);
   BVAE_LAUNCH_CHECK("final_im2col16");
   final_pack_wt_kernel<<<4, 256, 0, st>>>(w, wt);
   BVAE_LAUNCH_CHECK("final_pack_wt");
