@@ -727,6 +727,9 @@ extern "C" size_t bvae_conv3x3_wgrad_workspace(int B, int H, int W, int Cin, int
   if (conv_tc_wgrad_supported(H, W, Cin, Cout, stride)) {  // dtype is not known here: cover both kernels
     const WgradTcPlan pl = conv_tc_wgrad_plan(B, H, W, Cin, Cout, stride);
     if (pl.part_bytes + pl.bpart_bytes > bytes) bytes = pl.part_bytes + pl.bpart_bytes;
+  } else if (conv_wgrad_mma_small_supported(H, W, Cin, Cout, stride)) {
+    const WgradTcPlan pl = conv_wgrad_mma_small_plan(B, H, W, Cin, Cout, stride);
+    if (pl.part_bytes + pl.bpart_bytes > bytes) bytes = pl.part_bytes + pl.bpart_bytes;
   }
   return bytes;
 }
@@ -747,6 +750,18 @@ extern "C" int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, floa
     const int rc = conv_tc_wgrad(x, dy, part, dbias ? bpart : nullptr, pl, B, H, W, Cin, Cout, stride, st);
     if (rc != BVAE_OK) return rc;
     return launch_wgrad_reduce(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks, st);
+  }
+  {
+    const char* env = getenv("BVAE_CONV_SIMT");
+    if (!(env != nullptr && env[0] == '1') && x_dtype == BVAE_BF16 && dy_dtype == BVAE_BF16 &&
+        conv_wgrad_mma_small_supported(H, W, Cin, Cout, stride)) {   // narrow layers: warp-level MMA path
+      const WgradTcPlan pl = conv_wgrad_mma_small_plan(B, H, W, Cin, Cout, stride);
+      float* part = reinterpret_cast<float*>(ws);
+      float* bpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
+      const int rc = conv_wgrad_mma_small(x, dy, part, dbias ? bpart : nullptr, pl, B, H, W, Cin, Cout, stride, st);
+      if (rc != BVAE_OK) return rc;
+      return launch_wgrad_reduce(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks, st);
+    }
   }
   if (x_dtype == BVAE_F32 && dy_dtype == BVAE_F32)
     return wgrad_launch<float, float>(x, dy, dw, dbias, ws, B, H, W, Cin, Cout, stride, st);

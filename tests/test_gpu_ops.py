@@ -87,6 +87,13 @@ CONV_SHAPES = [
     (2, 16, 16, 256, 512, 2),
     (3, 8, 8, 64, 64, 1),
     (2, 24, 40, 64, 64, 1),
+    # narrow layers (overfit_capacity.yaml): warp-level MMA wgrad (conv_wgrad_mma.cu), stride 1 and 2
+    (2, 32, 16, 16, 16, 1),
+    (3, 32, 32, 32, 16, 1),
+    (2, 16, 16, 64, 32, 1),
+    (2, 64, 32, 16, 32, 2),
+    (3, 32, 32, 32, 64, 2),
+    (9, 64, 64, 16, 64, 1),     # more tiles than CTAs: several tiles per CTA
 ]
 
 
