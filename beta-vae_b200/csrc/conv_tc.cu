@@ -275,6 +275,7 @@ int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int
 int conv_tc_dgrad(const void* dy, const void* wpt, void* dx, int B, int H, int W, int Cin, int Cout, int stride,
                   cudaStream_t st) {
   if (stride == 1 && conv_halo_supported(H, W, Cout, Cin)) return conv_halo_launch(dy, wpt, nullptr, dx, B, H, W, Cout, Cin, 1, st);
+  if (stride == 2 && conv_s2_dgrad_halo_supported(H, W, Cin, Cout)) return conv_s2_dgrad_halo(dy, wpt, dx, B, H, W, Cin, Cout, st);
   TcMaps maps;
   TcParams p;
   memset(&p, 0, sizeof(p));

@@ -70,6 +70,10 @@ WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int strid
 int conv_tc_wgrad(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
                   int W, int Cin, int Cout, int stride, cudaStream_t st);
 
+// ---- stride-2 dgrad, halo formulation (conv_tc_s2dgrad.cu): H, W = extent of dx; N = Cin (dx), K = Cout (dy) ----
+bool conv_s2_dgrad_halo_supported(int H, int W, int N, int K);
+int conv_s2_dgrad_halo(const void* dy, const void* wpt_nk, void* dx, int B, int H, int W, int N, int K, cudaStream_t st);
+
 // ---- small-channel wgrad on the warp-level MMA path (conv_wgrad_mma.cu): 16/32/64 channels, not 64 x 64 ----
 bool conv_wgrad_mma_small_supported(int H, int W, int Cin, int Cout, int stride);
 WgradTcPlan conv_wgrad_mma_small_plan(int B, int H, int W, int Cin, int Cout, int stride);

@@ -94,6 +94,10 @@ CONV_SHAPES = [
     (2, 64, 32, 16, 32, 2),
     (3, 32, 32, 32, 64, 2),
     (9, 64, 64, 16, 64, 1),     # more tiles than CTAs: several tiles per CTA
+    # stride-2 dgrad, halo formulation (conv_tc_s2dgrad.cu): all four parity classes per CTA / one class per CTA
+    (5, 64, 32, 64, 64, 2),
+    (9, 64, 64, 128, 128, 2),
+    (2, 64, 64, 192, 256, 2),
 ]
 
 
