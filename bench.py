@@ -11,6 +11,10 @@ config's first-epoch settings), backward, gradient all-reduce (N>1), global-norm
 Adam.  Workload = beta-vae_b200/configs/beta_vae_se.yaml (128x128 grayscale, base 64, 4 blocks,
 latent 64), per-GPU batch = training.batch_size (32), synthetic 4-class MRI-shaped slices,
 random-init (Kaiming) weights.  Weak scaling: per-GPU batch fixed.
+`value`: inputs resident in HBM, the whole step replayed as one CUDA graph.  `e2e`: the same step through
+GraphedTrainStep with host buffers -- pinned uint8 image bytes copied host->device every step on the copy stream (one
+step ahead, converted to ToTensor's floats on the device), every step's loss scalars copied to pinned host memory and
+read on the host (one step behind).  `roofline`: the dominant kernel timed on the device with CUDA events.
 Prints ONE JSON line (rank 0).
 """
 import argparse

@@ -240,6 +240,10 @@ def test_gn_relu_se(shape, prec):
     dict(B=2, L=16, C=8, hw=8, mode="cap", beta=1.0, fb=0.0, reg=0.01),
     dict(B=33, L=64, C=32, hw=8, mode="cap", beta=1.0, fb=0.0, reg=0.0),
     dict(B=2, L=8, C=16, hw=4, mode="det", beta=1.0, fb=0.0, reg=0.02),
+    # batch > 128: the weight-gradient product runs several K passes (adds into the fp32 output), dh spans two row blocks
+    dict(B=160, L=8, C=16, hw=4, mode="cap", beta=1.0, fb=0.0, reg=0.0),
+    # F % 128 == 0 but P % 16 != 0: tensor-core path with the generic (non-patch) NHWC -> NCHW scatter
+    dict(B=5, L=8, C=128, hw=3, mode="beta", beta=1.0, fb=0.0, reg=0.0),
 ])
 def test_heads_reparam_kl(cfg, prec):
     ops = _ops()
@@ -304,7 +308,8 @@ def test_heads_reparam_kl(cfg, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("B,L,Cc,hw,zc", [(3, 8, 16, 4, 0.0), (2, 16, 8, 8, 0.7), (33, 64, 32, 8, 0.0)])
+@pytest.mark.parametrize("B,L,Cc,hw,zc", [(3, 8, 16, 4, 0.0), (2, 16, 8, 8, 0.7), (33, 64, 32, 8, 0.0),
+                                          (160, 8, 16, 4, 0.0), (5, 8, 128, 3, 0.5)])
 def test_fc_dec(B, L, Cc, hw, zc, prec):
     ops = _ops()
     dtype, tol = DT[prec]
