@@ -187,3 +187,36 @@ def test_inference_latent_sequences_match_reference_loops():
     zi = G.interpolation_latents(mu[0:1], mu[1:2], 6)
     for i, a in enumerate(torch.linspace(0, 1, 6)):
         assert torch.equal(zi[i:i + 1], (1 - a) * mu[0:1] + a * mu[1:2])
+
+
+def test_train_loop_stages_batches_one_ahead():
+    """train._staged_images hands batch i to the step only after batch i+1's host->device copy was started
+    (GraphedTrainStep.prefetch), keeps the loader's order, and passes through what it cannot stage."""
+    from training.train import _staged_images
+
+    class FakeStep:
+        def __init__(self):
+            self.x = torch.zeros(4, 1, 8, 8)
+            self.log = []
+
+        def prefetch(self, t):
+            self.log.append(("prefetch", int(t[0, 0, 0, 0])))
+            return ("staged", int(t[0, 0, 0, 0]))
+
+    step = FakeStep()
+    batches = [{"image": torch.full((4, 1, 8, 8), float(i))} for i in range(4)]
+    batches.append({"image": torch.full((3, 1, 8, 8), 4.0)})          # ragged tail: shape differs -> passed through
+    batches.append({"image": [torch.full((1, 8, 8), 5.0)] * 4})       # list of samples -> stacked, then staged
+    seen = []
+    for item in _staged_images(batches, step):
+        step.log.append(("step", item[1] if isinstance(item, tuple) else int(item[0, 0, 0, 0])))
+        seen.append(item)
+    assert [s[1] if isinstance(s, tuple) else int(s[0, 0, 0, 0]) for s in seen] == [0, 1, 2, 3, 4, 5]
+    assert isinstance(seen[4], torch.Tensor) and seen[4].shape[0] == 3
+    # every step i is preceded by the prefetch of batch i+1 (when that batch can be staged)
+    for i in (0, 1, 2):
+        assert step.log.index(("prefetch", i + 1)) < step.log.index(("step", i))
+    assert step.log.index(("prefetch", 5)) < step.log.index(("step", 4))
+    # without a graphed step the tensors come through untouched
+    plain = list(_staged_images(batches[:2], None))
+    assert all(isinstance(t, torch.Tensor) for t in plain) and len(plain) == 2
