@@ -187,11 +187,16 @@ class BetaVAE(nn.Module):
             return float(self.logvar_clamp[0]), float(self.logvar_clamp[1])
         return -10.0, 10.0
 
-    def _nhwc_input(self, x):
+    @staticmethod
+    def _unit_f32(x):
+        """fp32 image batch in [0, 1]; uint8 images (the dataset's PNG bytes) become ToTensor's floats on the device:
+        x / 255, bit-exact.  Done ONCE per call, so the encoder input and the loss targets are the same tensor."""
         if not x.is_cuda:
             raise RuntimeError("BetaVAE (bvae_b200) runs on CUDA tensors only; there is no CPU path")
-        # uint8 images (the dataset's PNG bytes) become ToTensor's floats on the device: x / 255, bit-exact
-        x = ops.u8_to_unit_f32(x.contiguous()) if x.dtype == torch.uint8 else x.contiguous().float()
+        return ops.u8_to_unit_f32(x.contiguous()) if x.dtype == torch.uint8 else x.contiguous().float()
+
+    def _nhwc_input(self, x):
+        x = self._unit_f32(x)
         b, c, h, w = x.shape
         return x.view(b, h, w, 1) if c == 1 else ops.nchw_to_nhwc(x, F32)
 
@@ -303,6 +308,7 @@ class BetaVAE(nn.Module):
             raise ValueError("invalid reconstruction_loss")
         dt = self._dt()
         dev = x.device
+        x = self._unit_f32(x)              # encoder input, reconstruction target and FFL target are all this tensor
         b = self.current_beta if beta is None else beta
         use_capacity = (capacity is not None) and (capacity_weight is not None)
         det = bool(self.deterministic)
@@ -316,7 +322,7 @@ class BetaVAE(nn.Module):
             fb=float(free_bits), det=det)
         feat = self._decode_features(z, dt)
         recon, base_recon = ops.FinalConvSigmoidRecon.apply(
-            feat, self.final_conv.weight, self.final_conv.bias, x.contiguous().float(), LOSS[self.recon_loss_type])
+            feat, self.final_conv.weight, self.final_conv.bias, x, LOSS[self.recon_loss_type])
 
         lp = torch.zeros((), device=dev)
         ff = torch.zeros((), device=dev)

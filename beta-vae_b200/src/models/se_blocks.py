@@ -27,8 +27,8 @@ class SEBlock(nn.Module):
         return self.fc[0].weight, self.fc[0].bias, self.fc[2].weight, self.fc[2].bias
 
     def forward(self, x):
-        """Stand-alone use on an NCHW tensor (not on the BetaVAE hot path, which calls the fused
-        kernel).  Runs the same arithmetic as the reference with device-side torch ops."""
-        n, c = x.shape[0], x.shape[1]
-        gate = self.fc(x.mean(dim=(2, 3))).view(n, c, 1, 1)
-        return x * gate
+        """The SE arithmetic exists only fused with GroupNorm + ReLU (``bvae_gn_relu_se_fwd``); there is no ATen or
+        CPU composition behind this module, so a stand-alone call fails loudly instead of silently running one."""
+        raise NotImplementedError(
+            "models.se_blocks.SEBlock (bvae_b200) owns the SE parameters; its arithmetic runs inside the fused "
+            "GroupNorm+ReLU+SE kernel of BetaVAE's blocks and is not available as a stand-alone module call")

@@ -6,7 +6,7 @@ FocalFrequencyLoss is on the default config's loss path (weight 0.5).  The trans
 F(pred - target)); everything after it -- |F|^2, the batch-mean scale, the focal weight, the mean and
 their backward -- is ``ops.FocalFrequencyCore`` (bvae_ffl_fwd / bvae_ffl_bwd), four launches instead of
 about twenty-five.  Its gradient reaches the fused final-conv kernel through the ``recon`` output of
-``ops.FinalConvSigmoidRecon``.  CPU tensors take the plain torch composition (stand-alone use only).
+``ops.FinalConvSigmoidRecon``.  There is no CPU path: CPU tensors raise.
 LPIPS is a third-party AlexNet (package + weights unavailable offline): out of scope."""
 import torch
 import torch.nn as nn
@@ -24,17 +24,12 @@ class FocalFrequencyLoss(nn.Module):
     def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if pred.shape != target.shape:
             raise ValueError(f"Shape mismatch: pred {pred.shape} vs target {target.shape}")
-        if pred.is_cuda:
-            from bvae_rt import ops
-            with torch.amp.autocast("cuda", enabled=False):
-                spec = torch.fft.rfft2(pred.float() - target.float(), norm="ortho")
-                return ops.FocalFrequencyCore.apply(torch.view_as_real(spec), pred.shape[-1], self.alpha, self.eps)
+        if not pred.is_cuda:
+            raise RuntimeError("FocalFrequencyLoss (bvae_b200) runs on CUDA tensors only; there is no CPU path")
+        from bvae_rt import ops
         with torch.amp.autocast("cuda", enabled=False):
-            spec = torch.fft.fft2(pred.float(), norm="ortho") - torch.fft.fft2(target.float(), norm="ortho")
-            power = spec.real.square() + spec.imag.square()
-            scale = power.mean(dim=(0, 2, 3), keepdim=True) + self.eps
-            weight = (power / scale).clamp_min(self.eps).pow(self.alpha)
-            return (weight * power).mean()
+            spec = torch.fft.rfft2(pred.float() - target.float(), norm="ortho")
+            return ops.FocalFrequencyCore.apply(torch.view_as_real(spec), pred.shape[-1], self.alpha, self.eps)
 
 
 class LPIPSLoss(nn.Module):

@@ -34,10 +34,10 @@ import torch
 import torch.distributed as dist
 
 from bvae_rt.data import synthetic_batch
-from bvae_rt.engine import GraphedTrainStep, TrainEngine, cosine_lr
+from bvae_rt.engine import GraphedTrainStep, StagedBatch, TrainEngine, cosine_lr
 from models.beta_vae import BetaVAE
 from training.schedulers import BetaScheduler, CapacityScheduler
-from utils.brain_tumor_utils.config_parser import get_config
+from utils.brain_tumor_utils.config_parser import get_config, set_config
 from utils.brain_tumor_utils.io import ensure_dirs, load_sharded_checkpoint, save_sharded_checkpoint
 from utils.brain_tumor_utils.logger import init_logger, log_config, log_metrics
 
@@ -112,7 +112,9 @@ def _payload(model, engine, epoch, total_steps, val_total):
 def _staged_images(loader, step_fn):
     """The loader's image batches, one step ahead: when batch i is handed to the step, the host->device copy of batch
     i+1 is already running on the copy stream (GraphedTrainStep.prefetch).  Without a graphed step, or for batches
-    that already live on the device, the tensors pass through unchanged."""
+    that already live on the device, the tensors pass through unchanged.  A batch whose shape differs from the graph's
+    static input (the last, partial batch of an epoch: the reference's DataLoader has no ``drop_last``,
+    datautils.py:78-91) is not staged either; ``train`` runs it through the un-captured step."""
     prev = None
     for batch_d in loader:
         x = batch_d["image"]
@@ -128,7 +130,9 @@ def _staged_images(loader, step_fn):
 
 
 def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_graph=True):
-    cfg = cfg or get_config()
+    if cfg is not None:
+        set_config(cfg)                  # the helpers below read the process-wide singleton, as the reference's do
+    cfg = get_config()
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank() if distributed else 0
     if not torch.cuda.is_available():
@@ -136,9 +140,9 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) if distributed else torch.cuda.current_device())
     torch.cuda.set_device(device)
     if rank == 0:
-        ensure_dirs(cfg)
-        init_logger(cfg)
-        log_config(cfg)
+        ensure_dirs()
+        init_logger()
+        log_config()
     set_seeds(cfg.data.seed)
 
     debug_cfg = getattr(cfg, "debug", None)
@@ -207,9 +211,11 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
         n_batches = 0
         for i, x in enumerate(_staged_images(train_loader, step_fn)):
             engine.lr = _lr_at(cfg, epochs, epoch - 1, total_steps)
-            if step_fn is not None:
+            full = isinstance(x, StagedBatch) or tuple(x.shape) == (batch, in_ch, size, size)
+            if step_fn is not None and full:
                 losses = step_fn(x, **kw)
             else:
+                # no graph, or a ragged (partial) batch: the same step enqueued kernel by kernel at the batch's own size
                 x = x.to(device, non_blocking=True)
                 engine.zero_grad()
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mixed):
@@ -241,7 +247,6 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
         model.eval()
         vsum = torch.zeros(6, device=device)
         vb = 0
-        val_mu = []
         vlast = None
         with torch.no_grad():
             for j, batch_d in enumerate(test_loader):
@@ -251,12 +256,20 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
                 l = model.loss(x.to(device, non_blocking=True), **kw)
                 vsum += torch.stack([l["total"], l["recon"], l["recon_base"], l["recon_lpips"].to(device),
                                      l["recon_ffl"].to(device), l["kl_mean"]]).float()
-                val_mu.append(l["mu"].cpu())
                 vlast = l
                 vb += 1
                 if debug_enabled and j + 1 >= debug_cfg.max_val_batches:
                     break
-        v = (vsum / max(1, vb)).tolist()
+        if distributed:
+            # every rank validates its own shard; the monitored value (checkpoint selection, early stopping) must be the
+            # same number on all ranks or they leave the epoch loop at different times and the next captured
+            # all-reduce never completes
+            cnt = torch.tensor([float(vb)], device=device)
+            dist.all_reduce(vsum)
+            dist.all_reduce(cnt)
+            v = (vsum / cnt.clamp_min(1.0)).tolist()
+        else:
+            v = (vsum / max(1, vb)).tolist()
         val_total = v[0]
         nan = float("nan")
         if rank == 0:

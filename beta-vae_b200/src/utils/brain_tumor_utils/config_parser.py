@@ -79,3 +79,12 @@ def get_config(path=None):
             if _config_cache is None:
                 _config_cache = freeze(load_config(path))
     return _config_cache
+
+
+def set_config(cfg):
+    """Install ``cfg`` (a mapping or an already frozen tree) as the process-wide singleton -- for callers that build
+    a config in code (tests, sweeps) instead of pointing ``CONFIG_PATH`` at a file.  Not in the reference."""
+    global _config_cache
+    with _config_lock:
+        _config_cache = cfg if isinstance(cfg, _Frozen) else freeze(cfg)
+    return _config_cache

@@ -7,9 +7,12 @@ un-sharded base file is removed.  Loading globs the shards, merges ``model_state
 the first shard; a plain single-file checkpoint is accepted as a fallback.  Files written here load with the
 reference's ``load_sharded_checkpoint`` and vice versa."""
 import glob
+import json
 import os
 
 import torch
+
+from .config_parser import get_config
 
 
 def _split_ext(base_path):
@@ -58,7 +61,55 @@ def load_sharded_checkpoint(base_path, map_location=None, num_shards=None):
     raise FileNotFoundError(f"No checkpoint found at {base_path} or shards")
 
 
-def ensure_dirs(cfg):
+def ensure_dirs():
+    """Create the output directories of the active config (reference: io.py:72-78, same no-argument call)."""
+    cfg = get_config()
     for key in ("outputs_dir", "models_dir", "figures_dir", "tables_dir"):
         os.makedirs(getattr(cfg.paths, key), exist_ok=True)
     os.makedirs(os.path.join(cfg.paths.outputs_dir, "logs"), exist_ok=True)
+
+
+def run_artifact_dir():
+    cfg = get_config()
+    d = os.path.join(cfg.paths.outputs_dir, cfg.paths.run_id)
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def model_checkpoint_path(epoch=None, tag=None):
+    """``<models_dir>/<run_id>_{tag | epoch<N> | latest}.pt`` (reference: io.py:86-94)."""
+    cfg = get_config()
+    os.makedirs(cfg.paths.models_dir, exist_ok=True)
+    stem = tag if tag else (f"epoch{epoch}" if epoch is not None else "latest")
+    return os.path.join(cfg.paths.models_dir, f"{cfg.paths.run_id}_{stem}.pt")
+
+
+def save_checkpoint(model, optimizer, epoch, metrics=None, tag=None, extra=None):
+    path = model_checkpoint_path(None if tag else epoch, tag=tag)
+    save_sharded_checkpoint(path, {
+        "epoch": epoch,
+        "model_state": model.state_dict(),
+        "optimizer_state": None if optimizer is None else optimizer.state_dict(),
+        "metrics": metrics or {},
+        "extra": extra or {},
+    }, num_shards=2)
+    return path
+
+
+def save_json(data, name):
+    out = os.path.join(get_config().paths.outputs_dir, f"{name}.json")
+    with open(out, "w") as f:
+        json.dump(data, f, indent=2)
+    return out
+
+
+def save_table(df, name):
+    path = os.path.join(get_config().paths.tables_dir, f"{name}.csv")
+    df.to_csv(path, index=False)
+    return path
+
+
+def save_figure(fig, name):
+    path = os.path.join(get_config().paths.figures_dir, f"{name}.png")
+    fig.savefig(path, bbox_inches="tight")
+    return path

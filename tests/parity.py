@@ -55,3 +55,30 @@ def check_vs_exact(name, got, ref_lp, exact, rtol, gnorm=0.0, floor=0.0, slack=4
                             f"{slack}*|ref-exact|={slack * e_ref:.3e})  (|exact|={n:.3e})")
     d = n if n > 0 else 1.0
     return e_got / d, e_ref / d
+
+
+def report_path(name="parity_r2.json"):
+    """Where the GPU parity tests drop their measured errors: gpurun_out/ of the tree they run in (it is merged back
+    to the build container; the committed copy lives under profiles/)."""
+    import os
+    root = os.environ.get("GRAFT_REPO_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, name)
+
+
+def report(key, record, name="parity_r2.json"):
+    """Merge one record into the JSON report (one key per test case)."""
+    import json
+    import os
+    path = report_path(name)
+    data = {}
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                data = json.load(f)
+        except Exception:  # noqa: BLE001
+            data = {}
+    data[key] = record
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)

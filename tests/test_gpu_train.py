@@ -59,3 +59,49 @@ def test_mixed_precision_graph_path_learns(tmp_path):
     hist = train(cfg=cfg)                                         # 2 eager steps, then CUDA-graph replays (bf16 kernels)
     assert len(hist) == 4
     assert hist[-1]["train_total"] < hist[0]["train_total"]
+
+
+class _ListLoader:
+    def __init__(self, batches):
+        self.batches = batches
+
+    def __iter__(self):
+        return iter(self.batches)
+
+    def __len__(self):
+        return len(self.batches)
+
+
+def test_ragged_tail_batch_runs_through_the_uncaptured_step(tmp_path):
+    """The reference's DataLoader has no drop_last (datautils.py:78-91): an epoch of N % batch != 0 samples ends with a
+    partial batch.  The captured graph has a fixed batch; the tail (here 5 and then 1 sample, host tensors) must be
+    trained on at its own size, not rejected and not broadcast into the static buffer."""
+    from training.train import train
+    cfg = _cfg(tmp_path, training__mixed_precision=True, debug__epochs=2, debug__max_train_batches=10)
+    g = torch.Generator().manual_seed(0)
+    mk = lambda n: {"image": torch.rand(n, 1, 128, 128, generator=g), "label": [0] * n}     # noqa: E731
+    loader = _ListLoader([mk(8), mk(8), mk(8), mk(5), mk(1)])
+    hist = train(cfg=cfg, train_loader=loader, test_loader=_ListLoader([mk(8), mk(3)]))
+    assert [h["steps"] for h in hist] == [5, 10]
+    assert all(torch.isfinite(torch.tensor([h["train_total"], h["val_total"]])).all() for h in hist)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_loss_on_uint8_images_equals_loss_on_their_floats(prec):
+    """loss(u8) must use x / 255 for the encoder input AND for both targets (reconstruction, focal-frequency)."""
+    from models.beta_vae import BetaVAE
+    from utils.brain_tumor_utils.config_parser import freeze
+    cfg = cfgs.small(loss__use_ffl=True, loss__ffl_weight=0.5)
+    torch.manual_seed(1)
+    m = BetaVAE(freeze(cfg), precision=prec).apply(cfgs.weight_init).cuda().train()
+    u8 = torch.randint(0, 256, (6, 1, 32, 32), dtype=torch.uint8, device="cuda")
+    eps = torch.randn(6, 8, device="cuda")
+    kw = dict(beta=2.0, capacity=None, free_bits=0.0, capacity_weight=None)
+    a = m.loss(u8, eps=eps, **kw)
+    b = m.loss(u8.float() / torch.full((), 255.0, device="cuda"), eps=eps, **kw)
+    for k in ("total", "recon", "recon_base", "recon_ffl", "kl_mean"):
+        assert float(a[k]) == float(b[k]), (k, float(a[k]), float(b[k]))
+    assert torch.equal(a["recon_img"], b["recon_img"])
+    with torch.no_grad():
+        m.eval()
+        assert float(m.loss(u8, eps=eps, **kw)["total"]) == float(a["total"])
