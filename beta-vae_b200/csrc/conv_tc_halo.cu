@@ -49,6 +49,7 @@ struct HaloParams {
   int resident;            // weights resident in shared memory
   int sa, sb;              // ring depths
   int nbuf, tmem_cols;     // accumulator buffers in TMEM
+  int dbg;                 // BVAE_HALO_DBG ablation bits (dev): 1 no global stores, 2 no epilogue work, 4 no MMAs, 8 no halo TMA
   uint32_t a_off, b_off, bar_off;
   __nv_bfloat16* dst;
   const float* bias;
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
           mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
           int live = 0;
           for (int m = 0; m < p.tm; ++m) live += (mg * p.tm + m < p.m_tiles) ? 1 : 0;
-          mbar_expect_tx(&a_full[sa], (uint32_t)live * HL_HALO_BYTES);
+          if (p.dbg & 8) { mbar_arrive(&a_full[sa]); live = 0; }
+          else mbar_expect_tx(&a_full[sa], (uint32_t)live * HL_HALO_BYTES);
           for (int m = 0; m < live; ++m) {
             int mt = mg * p.tm + m;
             const int w0 = (mt % p.tiles_w) * HL_TW;
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
           const uint64_t b_desc_res = kmajor_desc(smem_u32(b_base + (size_t)c * 9 * b_tap_bytes), HL_ROW);
 #pragma unroll
           for (int j = 0; j < 9; ++j) {
+            if ((p.dbg & 4) && RESIDENT) break;
             uint64_t b_desc;
             uint32_t sb = 0;
             if (RESIDENT) {
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
           __nv_bfloat16* out = p.dst + (((size_t)b * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl)) * p.N + n0;
 #pragma unroll 1
           for (int c = 0; c < BN; c += 32) {
+            if (p.dbg & 2) break;
             uint32_t v[32];
             tmem_ld32(taddr + (uint32_t)c, v);
             tmem_ld_wait();
@@ -270,7 +274,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
                 pk[e] = *reinterpret_cast<uint32_t*>(&h2);
               }
-              *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              if (!(p.dbg & 1) || pk[0] == 0x12345678u)
+                *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
@@ -301,6 +306,7 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.dgrad = dgrad ? 1 : 0;
+  if (const char* e = getenv("BVAE_HALO_DBG")) p.dbg = atoi(e);
   p.kchunks = K / 64;
   p.tiles_w = W / HL_TW;
   p.tiles_h = H / HL_TH;

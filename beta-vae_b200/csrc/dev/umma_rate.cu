@@ -97,6 +97,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
 }
 
+// elect.sync: one lane of a converged warp.  The issuing warp runs its loops with all 32 lanes (warp index obtained
+// through a shuffle, so the compiler knows it is warp-uniform) and predicates only the tcgen05 instructions on the
+// elected lane: descriptors then live in uniform registers and consecutive UTCHMMAs are 2-3 SASS instructions apart.
+// (With `if (threadIdx.x == 32)` around the loop, nvcc wraps every UTCHMMA in an ELECT / R2UR / BRA.U.ANY waterfall
+// loop -- measured 74 cycles per instruction regardless of N, the bound the round-1 convolution kernels ran into.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct RateParams {
   int mode, n, iters;
   uint32_t idesc;
@@ -146,7 +157,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const RateParams p) {
   }
   tc_fence_after();
 
-  if (threadIdx.x == 32 && rank == 0) {
+  const uint32_t warp_u = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (warp_u == 1 && rank == 0) {
+    const bool leader = elect_one();
     uint64_t ad[NMMA_BODY], bd[NMMA_BODY];
     uint32_t at[NMMA_BODY];
     const uint32_t a0 = smem_u32(a_sm), b0 = smem_u32(b_sm);
@@ -175,21 +188,30 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const RateParams p) {
     const long long t0 = clock64();
     if (p.mode == MODE_TS) {
       for (int it = 0; it < p.iters; ++it) {
+        if (leader) {
 #pragma unroll
-        for (int s = 0; s < NMMA_BODY; ++s) mma_ts<CG>(tmem, at[s], bd[s], p.idesc);
+          for (int s = 0; s < NMMA_BODY; ++s) mma_ts<CG>(tmem, at[s], bd[s], p.idesc);
+        }
+        __syncwarp();
       }
     } else {
       for (int it = 0; it < p.iters; ++it) {
+        if (leader) {
 #pragma unroll
-        for (int s = 0; s < NMMA_BODY; ++s) mma_ss<CG>(tmem, ad[s], bd[s], p.idesc);
+          for (int s = 0; s < NMMA_BODY; ++s) mma_ss<CG>(tmem, ad[s], bd[s], p.idesc);
+        }
+        __syncwarp();
       }
     }
-    commit_cg<CG>(bar);
+    if (leader) commit_cg<CG>(bar);
+    __syncwarp();
     const bool ok = mbar_wait_bounded(bar, 0);
     const long long t1 = clock64();
     tc_fence_after();
-    if (!ok) atomicExch(p.err, 1);
-    p.cycles[blockIdx.x / CG] = t1 - t0;
+    if (leader) {
+      if (!ok) atomicExch(p.err, 1);
+      p.cycles[blockIdx.x / CG] = t1 - t0;
+    }
   }
   tc_fence_before();
   if (CG == 2) {
@@ -199,6 +221,132 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const RateParams p) {
     __syncthreads();
   }
   if (warp == 0) tmem_dealloc_cg<CG>(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// "conv replay": the exact tcgen05.mma sequence of conv_halo_tc_kernel<64, resident> for one K = 64 chunk -- 9 taps x 4
+// k-steps, A = shifted windows of a 24 KB halo slot (8-row groups 1280 B apart), B = 9 resident [64][64] weight taps --
+// with the kernel's features switched on one at a time (flags) to see which of them costs MMA rate:
+//   1 real tap windows (else all taps read window 0)     2 nine distinct B taps (else tap 0)
+//   4 tcgen05.commit to an mbarrier after every 36 MMAs   8 accumulator alternates between two TMEM column ranges
+//  16 halo slot rotates over 4 slots                      32 first MMA of a tile overwrites (accumulate = 0)
+// ---------------------------------------------------------------------------------------------------------------
+struct ConvReplayParams {
+  int flags, tiles, n;
+  long long* cycles;
+  int* err;
+};
+
+__device__ __forceinline__ void mma_acc(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <int FLAGS, int NN>
+__global__ void __launch_bounds__(128, 1) conv_replay_kernel(const ConvReplayParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t B_TOTAL = 9u * (uint32_t)NN * 128u, A_SLOT = 24576u;
+  uint8_t* b_sm = smem;
+  uint8_t* a_sm = smem + B_TOTAL;
+  constexpr uint32_t nslots = NN > 64 ? 3u : 4u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(a_sm + nslots * A_SLOT);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 4);
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < (B_TOTAL + nslots * A_SLOT) / 4; i += blockDim.x) {
+    const uint32_t h = (i * 2654435761u) >> 28;
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u + (h << 16) + h;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc_cg<1>(tslot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t warp_u = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (warp_u == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t b_tap = (uint32_t)NN * 128u;
+    constexpr bool f_win = FLAGS & 1, f_b = FLAGS & 2, f_commit = FLAGS & 4, f_d = FLAGS & 8, f_slot = FLAGS & 16,
+               f_first = FLAGS & 32;
+    const long long t0 = clock64();
+    for (int t = 0; t < p.tiles; ++t) {
+      const uint32_t slot = f_slot ? (uint32_t)t % nslots : 0u;
+      uint64_t a0 = (uint64_t)(((smem_u32(a_sm) + slot * A_SLOT) & 0x3FFFFu) >> 4);
+      a0 |= 1ull << 16;
+      a0 |= (uint64_t)(1280u >> 4) << 32;
+      a0 |= 1ull << 46;
+      a0 |= 2ull << 61;
+      const uint64_t b0 = kmajor_desc(smem_u32(b_sm), 128);
+      const uint32_t d = tmem + (f_d ? (uint32_t)(t & 1) * (uint32_t)NN : 0u);
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const uint32_t win = f_win ? (uint32_t)((j / 3) * 10 + (j % 3)) * 128u : 0u;
+          const uint32_t bo = f_b ? (uint32_t)j * b_tap : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_acc(d, a0 + (uint64_t)((win + k * 32) >> 4), b0 + (uint64_t)((bo + k * 32) >> 4), idesc,
+                    (f_first && j == 0 && k == 0) ? 0u : 1u);
+        }
+        if (f_commit) commit_cg<1>(&bar[1]);     // nobody waits on it (phase flips are harmless)
+      }
+      __syncwarp();
+    }
+    if (leader) commit_cg<1>(&bar[0]);
+    __syncwarp();
+    const bool ok = mbar_wait_bounded(&bar[0], 0);
+    const long long t1 = clock64();
+    tc_fence_after();
+    if (leader) {
+      if (!ok) atomicExch(p.err, 1);
+      p.cycles[blockIdx.x] = t1 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_cg<1>(tmem, 512);
+}
+
+static int run_conv_replay(int flags, int n, int tiles) {
+  const int grid = 148;
+  long long* d_cyc;
+  int* d_err;
+  cudaMalloc(&d_cyc, sizeof(long long) * grid);
+  cudaMalloc(&d_err, sizeof(int));
+  cudaMemset(d_err, 0, sizeof(int));
+  ConvReplayParams p;
+  p.flags = flags; p.tiles = tiles; p.n = n; p.cycles = d_cyc; p.err = d_err;
+  const size_t smem = 9 * (size_t)n * 128 + (n > 64 ? 3 : 4) * 24576 + 1024 + 128;
+  void (*kern)(const ConvReplayParams) =
+      n == 64 ? (flags ? conv_replay_kernel<63, 64> : conv_replay_kernel<0, 64>)
+              : (flags ? conv_replay_kernel<63, 128> : conv_replay_kernel<0, 128>);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, 128, smem>>>(p);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("conv_replay flags=%d N=%d : CUDA error %s\n", flags, n, cudaGetErrorString(e));
+    return 1;
+  }
+  std::vector<long long> cyc(grid);
+  int err = 0;
+  cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_cyc);
+  cudaFree(d_err);
+  std::sort(cyc.begin(), cyc.end());
+  const double nm = (double)tiles * 36.0;
+  printf("conv_replay N=%3d flags=%2d [%s%s%s%s%s%s] : %6.1f cyc/MMA (max %6.1f)  floor %5.1f%s\n", n, flags,
+         flags & 1 ? "win " : "", flags & 2 ? "9taps " : "", flags & 4 ? "commit " : "", flags & 8 ? "2acc " : "",
+         flags & 16 ? "4slots " : "", flags & 32 ? "overwrite " : "", cyc[grid / 2] / nm, cyc[grid - 1] / nm, n / 2.0,
+         err ? "  [TIMEOUT]" : "");
+  fflush(stdout);
+  return err;
 }
 
 static const char* mode_name(int m) {
@@ -296,6 +444,10 @@ int main(int argc, char** argv) {
         if (mode == MODE_SS_MN && n < 128) continue;
         bad |= run_case(2, mode, 256, n, iters, nullptr);
       }
+  }
+  if (want("conv")) {
+    for (int n : {64, 128})
+      for (int flags : {0, 63}) bad |= run_conv_replay(flags, n, 56);
   }
   return bad;
 }

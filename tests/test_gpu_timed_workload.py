@@ -7,7 +7,8 @@ oracle on the same weights, inputs and injected eps:
     oracle under bf16 autocast;
   * all parameter gradients the replayed step left in the engine's flat buffer: every tensor within 1e-2 of fp64
     (or, for ill-conditioned tensors, within 4x of the bf16-autocast reference's own distance from fp64 --
-    tests/parity.py), and the whole gradient within 1e-2;
+    tests/parity.py), and the whole gradient within max(1e-2, 1.25x the bf16-autocast reference's own distance from
+    fp64): measured 1.32e-2 against the reference's own 1.24e-2 at the default config, i.e. the precision's error;
   * the graph's outputs equal an eager step on the same inputs bit for bit (same kernels, same order).
 
 Batch-dependent kernel plans (persistent-CTA tile counts, GroupNorm cluster sizes, split-K factors) are the ones the
@@ -103,7 +104,9 @@ def test_graph_replayed_bf16_step_matches_oracle(case):
           f"(bf16 oracle's own {whole_ref:.2e}); worst {worst[0]} {worst[1]:.2e} (own {worst[2]:.2e}); "
           f"{len(rec['tensors_above_1e-2'])}/{len(rows)} tensors above 1e-2")
     assert not failures, failures
-    assert whole <= rtol, whole
+    # whole gradient: 1e-2 where bf16 itself allows it; at this depth the reference under bf16 autocast is itself
+    # ~1.2e-2 from its fp64 evaluation (reported above), so the bound is the larger of the two
+    assert whole <= max(rtol, 1.25 * whole_ref), (whole, whole_ref)
 
     # the replay and an un-captured step on the same inputs run the same kernels: bit-identical gradients
     engine.flat_p.copy_(flat_before)
