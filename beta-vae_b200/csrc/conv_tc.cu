@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* accum_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   // tile coordinates
   int tile = blockIdx.x;
   const int tw_i = tile % p.tiles_w;
@@ -73,38 +73,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      tma_prefetch_desc(&maps.w);
-      int s = 0, t = 0, kc = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        const TcTap tap = p.taps[cls][t];
-        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + a_bytes;
+    // ===== TMA producer (all lanes run the loop, the elected lane issues; see elect_one() in tc_ptx.cuh) =====
+    const bool leader = elect_one();
+    if (leader) tma_prefetch_desc(&maps.w);
+    int s = 0, t = 0, kc = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const TcTap tap = p.taps[cls][t];
+      uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+      uint8_t* b_dst = a_dst + a_bytes;
+      if (leader) {
         mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
         tma_load_4d(&maps.src[tap.map], &full_bar[s], a_dst, kc * p.kc, w0 + tap.dj, h0 + tap.di, b0);
         tma_load_3d(&maps.w, &full_bar[s], b_dst, kc * p.kc, n0, tap.widx);
-        if (++kc == p.kchunks) { kc = 0; ++t; }
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (++kc == p.kchunks) { kc = 0; ++t; }
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t row_bytes = p.kc * 2;
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t smem0 = smem_u32(smem);
-      const uint64_t desc_hi = kmajor_desc(0, row_bytes);     // everything but the address field
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem0 + (uint32_t)s * stage_bytes;
-        const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)((a_addr + a_bytes) >> 4);
+    // ===== MMA issuer (all lanes run the loop, the elected lane issues) =====
+    const bool leader = elect_one();
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t row_bytes = p.kc * 2;
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint64_t desc_hi = kmajor_desc(0, row_bytes);     // everything but the address field
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem0 + (uint32_t)s * stage_bytes;
+      const uint64_t adesc = desc_hi + (uint64_t)(a_addr >> 4), bdesc = desc_hi + (uint64_t)((a_addr + a_bytes) >> 4);
+      if (leader) {
         // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in 16-byte units
         umma_bf16(tmem_base, adesc, bdesc, idesc, it != 0 ? 1u : 0u);
         if (p.kc >= 32) umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
@@ -113,10 +116,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           umma_bf16(tmem_base, adesc + 6, bdesc + 6, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(accum_bar);        // accumulator complete
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
+    if (leader) umma_commit(accum_bar);        // accumulator complete
+    __syncwarp();
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
   float* bias_sm = reinterpret_cast<float*>(smem + p.bar_off + 256);  // [N] (zeros when there is no bias)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const uint32_t a_slot_bytes = (uint32_t)p.tm * HL_HALO_SLOT;
   constexpr uint32_t b_tap_bytes = (uint32_t)BN * HL_ROW;
 
@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (all 32 lanes run the loop; the elected lane issues) =====
+    const bool leader = elect_one();
+    if (leader) {
       tma_prefetch_desc(&maps.x);
       tma_prefetch_desc(&maps.w);
       if (RESIDENT) {
@@ -144,94 +145,112 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
           for (int j = 0; j < 9; ++j)
             tma_load_3d(&maps.w, b_res, b_base + (size_t)(c * 9 + j) * b_tap_bytes, c * 64, n0, p.dgrad ? 8 - j : j);
       }
-      uint32_t ia = 0, ib = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const int nt = u % p.n_tiles, mg = u / p.n_tiles;
-        const int n0 = nt * BN;
-        for (int c = 0; c < p.kchunks; ++c, ++ia) {
-          const uint32_t sa = ia % p.sa;
-          mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
-          int live = 0;
-          for (int m = 0; m < p.tm; ++m) live += (mg * p.tm + m < p.m_tiles) ? 1 : 0;
-          if (p.dbg & 8) { mbar_arrive(&a_full[sa]); live = 0; }
+    }
+    __syncwarp();
+    uint32_t ia = 0, ib = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const int nt = u % p.n_tiles, mg = u / p.n_tiles;
+      const int n0 = nt * BN;
+      for (int c = 0; c < p.kchunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.sa;
+        mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
+        int live = 0;
+        for (int m = 0; m < p.tm; ++m) live += (mg * p.tm + m < p.m_tiles) ? 1 : 0;
+        if (p.dbg & 8) live = 0;
+        if (leader) {
+          if (p.dbg & 8) mbar_arrive(&a_full[sa]);
           else mbar_expect_tx(&a_full[sa], (uint32_t)live * HL_HALO_BYTES);
-          for (int m = 0; m < live; ++m) {
-            int mt = mg * p.tm + m;
-            const int w0 = (mt % p.tiles_w) * HL_TW;
-            mt /= p.tiles_w;
-            const int h0 = (mt % p.tiles_h) * HL_TH;
-            const int b = mt / p.tiles_h;
+        }
+        for (int m = 0; m < live; ++m) {
+          int mt = mg * p.tm + m;
+          const int w0 = (mt % p.tiles_w) * HL_TW;
+          mt /= p.tiles_w;
+          const int h0 = (mt % p.tiles_h) * HL_TH;
+          const int b = mt / p.tiles_h;
+          if (leader)
             tma_load_4d(&maps.x, &a_full[sa], a_ring + (size_t)sa * a_slot_bytes + (size_t)m * HL_HALO_SLOT, c * 64, w0 - 1,
                         h0 - 1, b);
-          }
-          if (!RESIDENT) {
+        }
+        if (!RESIDENT) {
 #pragma unroll 1
-            for (int j = 0; j < 9; ++j, ++ib) {
-              const uint32_t sb = ib % p.sb;
-              mbar_wait(&b_empty[sb], ((ib / p.sb) & 1u) ^ 1u);
+          for (int j = 0; j < 9; ++j, ++ib) {
+            const uint32_t sb = ib % p.sb;
+            mbar_wait(&b_empty[sb], ((ib / p.sb) & 1u) ^ 1u);
+            if (leader) {
               mbar_expect_tx(&b_full[sb], b_tap_bytes);
               tma_load_3d(&maps.w, &b_full[sb], b_base + (size_t)sb * b_tap_bytes, c * 64, n0, p.dgrad ? 8 - j : j);
             }
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread; the tap / k loops are unrolled with constant descriptor offsets) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc =
-          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      if (RESIDENT) {
-        mbar_wait(b_res, 0);
+    // ===== MMA issuer (all 32 lanes run the loop, the elected lane issues; the tap / k loops are unrolled with
+    //       constant descriptor offsets, so consecutive tcgen05.mma are one or two uniform adds apart) =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (RESIDENT) {
+      mbar_wait(b_res, 0);
+      tc_fence_after();
+    }
+    uint32_t ia = 0, ib = 0, iu = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      const int mg = u / p.n_tiles;
+      const uint32_t buf = iu % p.nbuf;
+      mbar_wait(&acc_empty[buf], ((iu / p.nbuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem_base + buf * (uint32_t)(p.tm * BN);
+      const bool two = (mg * p.tm + 1 < p.m_tiles && p.tm == 2);
+      for (int c = 0; c < p.kchunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.sa;
+        mbar_wait(&a_full[sa], (ia / p.sa) & 1u);
         tc_fence_after();
-      }
-      uint32_t ia = 0, ib = 0, iu = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-        const int mg = u / p.n_tiles;
-        const uint32_t buf = iu % p.nbuf;
-        mbar_wait(&acc_empty[buf], ((iu / p.nbuf) & 1u) ^ 1u);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t acc = tmem_base + buf * (uint32_t)(p.tm * BN);
-        const int live = (mg * p.tm + 1 < p.m_tiles && p.tm == 2) ? 2 : 1;
-        for (int c = 0; c < p.kchunks; ++c, ++ia) {
-          const uint32_t sa = ia % p.sa;
-          mbar_wait(&a_full[sa], (ia / p.sa) & 1u);
-          tc_fence_after();
-          const uint64_t a_desc0 = kmajor_desc_sbo(smem_u32(a_ring + (size_t)sa * a_slot_bytes), HL_GROUP_STRIDE);
+        const uint64_t a_desc0 = kmajor_desc_sbo(smem_u32(a_ring + (size_t)sa * a_slot_bytes), HL_GROUP_STRIDE);
+        const uint32_t acc_on = c != 0 ? 1u : 0u;
+        if (RESIDENT) {
           const uint64_t b_desc_res = kmajor_desc(smem_u32(b_base + (size_t)c * 9 * b_tap_bytes), HL_ROW);
+          if (leader && !(p.dbg & 4)) {
 #pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            if ((p.dbg & 4) && RESIDENT) break;
-            uint64_t b_desc;
-            uint32_t sb = 0;
-            if (RESIDENT) {
-              b_desc = b_desc_res + (uint64_t)((j * b_tap_bytes) >> 4);
-            } else {
-              sb = ib % p.sb;
-              mbar_wait(&b_full[sb], (ib / p.sb) & 1u);
-              tc_fence_after();
-              b_desc = kmajor_desc(smem_u32(b_base + (size_t)sb * b_tap_bytes), HL_ROW);
-              ++ib;
-            }
-            constexpr uint32_t dummy = 0;
-            (void)dummy;
-            const uint32_t win = (uint32_t)((j / 3) * HL_HW + (j % 3)) * HL_ROW;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(acc, a_desc0 + (uint64_t)((win + k * 32) >> 4), b_desc + (uint64_t)(k * 2), idesc,
-                        (j | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
-            if (live == 2) {
+            for (int j = 0; j < 9; ++j) {
+              const uint64_t b_desc = b_desc_res + (uint64_t)((j * b_tap_bytes) >> 4);
+              const uint32_t win = (uint32_t)((j / 3) * HL_HW + (j % 3)) * HL_ROW;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(acc + BN, a_desc0 + (uint64_t)((HL_HALO_SLOT + win + k * 32) >> 4), b_desc + (uint64_t)(k * 2),
-                          idesc, (j | k) != 0 ? 1u : (c != 0 ? 1u : 0u));
+                umma_bf16(acc, a_desc0 + (uint64_t)((win + k * 32) >> 4), b_desc + (uint64_t)(k * 2), idesc,
+                          (j | k) != 0 ? 1u : acc_on);
             }
-            if (!RESIDENT) umma_commit(&b_empty[sb]);
           }
-          umma_commit(&a_empty[sa]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 9; ++j, ++ib) {
+            const uint32_t sb = ib % p.sb;
+            mbar_wait(&b_full[sb], (ib / p.sb) & 1u);
+            tc_fence_after();
+            const uint64_t b_desc = kmajor_desc(smem_u32(b_base + (size_t)sb * b_tap_bytes), HL_ROW);
+            const uint32_t win = (uint32_t)((j / 3) * HL_HW + (j % 3)) * HL_ROW;
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(acc, a_desc0 + (uint64_t)((win + k * 32) >> 4), b_desc + (uint64_t)(k * 2), idesc,
+                          (j | k) != 0 ? 1u : acc_on);
+              if (two) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(acc + BN, a_desc0 + (uint64_t)((HL_HALO_SLOT + win + k * 32) >> 4), b_desc + (uint64_t)(k * 2),
+                            idesc, (j | k) != 0 ? 1u : acc_on);
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+          }
         }
-        umma_commit(&acc_full[buf]);
+        if (leader) umma_commit(&a_empty[sa]);
+        __syncwarp();
       }
+      if (leader) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -435,7 +454,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
   constexpr uint32_t TMEM_COLS = 4 * N;                    // two accumulators per buffer, two buffers
   constexpr uint32_t B_CHUNK = (uint32_t)N * HL_ROW;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.sa; ++s) {
@@ -456,45 +475,52 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // producer: all lanes run the loop, the elected lane issues the TMA loads (see elect_one() in tc_ptx.cuh)
+    const bool leader = elect_one();
+    if (leader) {
       tma_prefetch_desc(&maps.x);
       tma_prefetch_desc(&maps.w);
       mbar_expect_tx(b_res, (uint32_t)p.kchunks * B_CHUNK);
       for (int c = 0; c < p.kchunks; ++c) tma_load_3d(&maps.w, b_res, b_base + (size_t)c * B_CHUNK, c * 64, 0, 0);
-      uint32_t ia = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        int mt = u;
-        const int w0 = (mt % p.tiles_w) * HL_TW;
-        mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * HL_TH;
-        const int b = mt / p.tiles_h;
-        for (int c = 0; c < p.kchunks; ++c, ++ia) {
-          const uint32_t sa = ia % p.sa;
-          mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
+    }
+    __syncwarp();
+    uint32_t ia = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int mt = u;
+      const int w0 = (mt % p.tiles_w) * HL_TW;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * HL_TH;
+      const int b = mt / p.tiles_h;
+      for (int c = 0; c < p.kchunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.sa;
+        mbar_wait(&a_empty[sa], ((ia / p.sa) & 1u) ^ 1u);
+        if (leader) {
           mbar_expect_tx(&a_full[sa], HL_HALO_BYTES);
           tma_load_4d(&maps.x, &a_full[sa], a_ring + (size_t)sa * HL_HALO_SLOT, c * 64, w0 - 1, h0 - 1, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc =
-          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      mbar_wait(b_res, 0);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(b_res, 0);
+    tc_fence_after();
+    uint32_t ia = 0, iu = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      const uint32_t buf = iu & 1u;
+      mbar_wait(&acc_empty[buf], ((iu >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      uint32_t ia = 0, iu = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-        const uint32_t buf = iu & 1u;
-        mbar_wait(&acc_empty[buf], ((iu >> 1) & 1u) ^ 1u);
+      const uint32_t acc = tmem_base + buf * (uint32_t)(2 * N);
+      for (int c = 0; c < p.kchunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.sa;
+        mbar_wait(&a_full[sa], (ia / p.sa) & 1u);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * (uint32_t)(2 * N);
-        for (int c = 0; c < p.kchunks; ++c, ++ia) {
-          const uint32_t sa = ia % p.sa;
-          mbar_wait(&a_full[sa], (ia / p.sa) & 1u);
-          tc_fence_after();
-          const uint64_t a_desc0 = kmajor_desc(smem_u32(a_ring + (size_t)sa * HL_HALO_SLOT), HL_ROW);   // dense rows
-          const uint64_t b_desc0 = kmajor_desc(smem_u32(b_base + (size_t)c * B_CHUNK), HL_ROW);
-          const uint32_t acc_on = c != 0 ? 1u : 0u;
+        const uint64_t a_desc0 = kmajor_desc(smem_u32(a_ring + (size_t)sa * HL_HALO_SLOT), HL_ROW);   // dense rows
+        const uint64_t b_desc0 = kmajor_desc(smem_u32(b_base + (size_t)c * B_CHUNK), HL_ROW);
+        const uint32_t acc_on = c != 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             umma_bf16(acc, a_desc0 + (uint64_t)((k * 32) >> 4), b_desc0 + (uint64_t)(k * 2), idesc, k != 0 ? 1u : acc_on);
@@ -503,8 +529,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
           }
           umma_commit(&a_empty[sa]);
         }
-        umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (leader) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

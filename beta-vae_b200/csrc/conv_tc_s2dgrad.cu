@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
   constexpr int NGRP = 4 / CG;
   constexpr int NSLOT = CG == 4 ? 9 : 5;            // weight slots per K chunk
   constexpr uint32_t TMEM_COLS = 2 * CG * SD_BN;    // 512 / 256
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const int fix = blockIdx.x % p.nfix;              // gridDim.x is a multiple of nfix: fixed for all units of the CTA
   const int grp = fix % NGRP, n0 = (fix / NGRP) * SD_BN;
 
@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // producer: all lanes run the loop, the elected lane issues the TMA loads (see elect_one() in tc_ptx.cuh)
+    const bool leader = elect_one();
+    if (leader) {
       tma_prefetch_desc(&maps.dy);
       tma_prefetch_desc(&maps.w);
       int ntap_cta = 0;
@@ -149,38 +151,44 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
             tma_load_3d(&maps.w, b_res, b_base + (size_t)(c * NSLOT + slot0 + j) * SD_TAP_BYTES, c * 64, n0,
                         sd_r(cls, j) * 3 + sd_s(cls, j));
         }
-      uint32_t ia = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        int mt = u / p.nfix;
-        const int w0 = (mt % p.tiles_w) * SD_TW;
-        mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * SD_TH;
-        const int b = mt / p.tiles_h;
-        for (int c = 0; c < p.kchunks; ++c, ++ia) {
-          const uint32_t sa = ia % p.stages;
-          mbar_wait(&a_empty[sa], ((ia / p.stages) & 1u) ^ 1u);
+    }
+    __syncwarp();
+    uint32_t ia = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      int mt = u / p.nfix;
+      const int w0 = (mt % p.tiles_w) * SD_TW;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * SD_TH;
+      const int b = mt / p.tiles_h;
+      for (int c = 0; c < p.kchunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.stages;
+        mbar_wait(&a_empty[sa], ((ia / p.stages) & 1u) ^ 1u);
+        if (leader) {
           mbar_expect_tx(&a_full[sa], SD_BYTES);
           tma_load_4d(&maps.dy, &a_full[sa], a_ring + (size_t)sa * SD_SLOT, c * 64, w0, h0, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(b_res, 0);
+    // MMA issuer: all lanes run the loop, the elected lane issues
+    const bool leader = elect_one();
+    mbar_wait(b_res, 0);
+    tc_fence_after();
+    uint32_t ia = 0, iu = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      const uint32_t buf = iu & 1u;
+      mbar_wait(&acc_empty[buf], ((iu >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      uint32_t ia = 0, iu = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-        const uint32_t buf = iu & 1u;
-        mbar_wait(&acc_empty[buf], ((iu >> 1) & 1u) ^ 1u);
+      const uint32_t acc = tmem_base + buf * (uint32_t)(CG * SD_BN);
+      for (int c = 0; c < p.kchunks; ++c, ++ia) {
+        const uint32_t sa = ia % p.stages;
+        mbar_wait(&a_full[sa], (ia / p.stages) & 1u);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * (uint32_t)(CG * SD_BN);
-        for (int c = 0; c < p.kchunks; ++c, ++ia) {
-          const uint32_t sa = ia % p.stages;
-          mbar_wait(&a_full[sa], (ia / p.stages) & 1u);
-          tc_fence_after();
-          const uint64_t a_desc0 = sd_kdesc(smem_u32(a_ring + (size_t)sa * SD_SLOT), SD_SBO);
-          const uint64_t b_desc0 = kmajor_desc(smem_u32(b_base + (size_t)c * NSLOT * SD_TAP_BYTES), SD_ROW);
-          const uint32_t acc_on = c != 0 ? 1u : 0u;
+        const uint64_t a_desc0 = sd_kdesc(smem_u32(a_ring + (size_t)sa * SD_SLOT), SD_SBO);
+        const uint64_t b_desc0 = kmajor_desc(smem_u32(b_base + (size_t)c * NSLOT * SD_TAP_BYTES), SD_ROW);
+        const uint32_t acc_on = c != 0 ? 1u : 0u;
+        if (leader) {
           if constexpr (CG == 4) {
             sd_issue_class<0>(acc, a_desc0, b_desc0, sd_slot0(0), acc_on);
             sd_issue_class<1>(acc + SD_BN, a_desc0, b_desc0, sd_slot0(1), acc_on);
@@ -195,8 +203,10 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
           }
           umma_commit(&a_empty[sa]);
         }
-        umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (leader) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   uint64_t* accum_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const int rb0 = blockIdx.x * p.slots;  // first 128-row block of this CTA
   const int n0 = blockIdx.y * p.bn;
   const int split = blockIdx.z;
@@ -81,25 +81,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0 && iters > 0) {
-      int nunits = 0;
-      for (int s = 0; s < nslots; ++s)
-        for (int h = 0; h < 2; ++h)
-          if (2 * (rb0 + s) + h < p.units) ++nunits;
-      const uint32_t tx_bytes = (uint32_t)(nb + nunits) * WG_BOX;
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&empty_bar[st], ph ^ 1u);
-        int tile = t_beg + it;
-        const int w0 = (tile % p.tiles_w) * p.tw;
-        tile /= p.tiles_w;
-        const int h0 = (tile % p.tiles_h) * p.th;
-        const int b0 = (tile / p.tiles_h) * p.tn;
-        uint8_t* base = smem + (size_t)st * stage_bytes;
+    // producer: all lanes run the loop, the elected lane issues (see elect_one() in tc_ptx.cuh)
+    const bool leader = elect_one();
+    int nunits = 0;
+    for (int s = 0; s < nslots; ++s)
+      for (int h = 0; h < 2; ++h)
+        if (2 * (rb0 + s) + h < p.units) ++nunits;
+    const uint32_t tx_bytes = (uint32_t)(nb + nunits) * WG_BOX;
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(&empty_bar[st], ph ^ 1u);
+      int tile = t_beg + it;
+      const int w0 = (tile % p.tiles_w) * p.tw;
+      tile /= p.tiles_w;
+      const int h0 = (tile % p.tiles_h) * p.th;
+      const int b0 = (tile / p.tiles_h) * p.tn;
+      uint8_t* base = smem + (size_t)st * stage_bytes;
+      uint8_t* xb = base + (size_t)nb * WG_BOX;
+      if (leader) {
         mbar_expect_tx(&full_bar[st], tx_bytes);
         for (int j = 0; j < nb; ++j) tma_load_4d(&maps.dy, &full_bar[st], base + (size_t)j * WG_BOX, n0 + 64 * j, w0, h0, b0);
-        uint8_t* xb = base + (size_t)nb * WG_BOX;
         for (int s = 0; s < nslots; ++s)
           for (int h = 0; h < 2; ++h) {
             const int u = 2 * (rb0 + s) + h;
@@ -109,19 +111,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                         w0 + tap.dj, h0 + tap.di, b0);
           }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && iters > 0) {
-      // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&full_bar[st], ph);
-        tc_fence_after();
-        const uint32_t dy_addr = smem_u32(smem + (size_t)st * stage_bytes);
-        const uint32_t x_addr = dy_addr + (uint32_t)nb * WG_BOX;
+    const bool leader = elect_one();
+    // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(&full_bar[st], ph);
+      tc_fence_after();
+      const uint32_t dy_addr = smem_u32(smem + (size_t)st * stage_bytes);
+      const uint32_t x_addr = dy_addr + (uint32_t)nb * WG_BOX;
+      if (leader) {
         for (int s = 0; s < nslots; ++s) {
 #pragma unroll
           for (int k = 0; k < WG_PIX / 16; ++k) {
@@ -133,8 +137,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         }
         umma_commit(&empty_bar[st]);
       }
-      umma_commit(accum_bar);
+      __syncwarp();
     }
+    if (leader && iters > 0) umma_commit(accum_bar);
+    __syncwarp();
   } else if (iters > 0) {
     const int q = warp & 3;
     const int m = q * 32 + lane;  // accumulator row: unit half (m / 64), channel within chunk (m % 64)
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* accum_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const int cc = blockIdx.x % p.cin_chunks, cb = blockIdx.x / p.cin_chunks;
   const int split = blockIdx.y;
   const int t_beg = split * p.tiles_per_split;
@@ -233,55 +239,60 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // producer: all lanes run the loop, the elected lane issues the TMA loads
+    const bool leader = elect_one();
+    if (leader) {
       for (int q = 0; q < p.nplanes; ++q) tma_prefetch_desc(&maps.x[q]);
       tma_prefetch_desc(&maps.dy);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&empty_bar[st], ph ^ 1u);
-        int tile = t_beg + it;
-        const int w0 = (tile % p.tiles_w) * 8;
-        tile /= p.tiles_w;
-        const int h0 = (tile % p.tiles_h) * p.th;
-        const int b = tile / p.tiles_h;
-        uint8_t* base = smem + (size_t)st * p.stage_bytes;
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&empty_bar[st], ph ^ 1u);
+      int tile = t_beg + it;
+      const int w0 = (tile % p.tiles_w) * 8;
+      tile /= p.tiles_w;
+      const int h0 = (tile % p.tiles_h) * p.th;
+      const int b = tile / p.tiles_h;
+      uint8_t* base = smem + (size_t)st * p.stage_bytes;
+      if (leader) {
         mbar_expect_tx(&full_bar[st], (uint32_t)p.nplanes * p.box_bytes + p.dy_bytes);
         for (int q = 0; q < p.nplanes; ++q)
           tma_load_4d(&maps.x[q], &full_bar[st], base + (size_t)q * p.slot_bytes, cc * 64, w0 - 1, h0 - 1, b);
         tma_load_4d(&maps.dy, &full_bar[st], base + (size_t)p.nplanes * p.slot_bytes, cb * 64, w0, h0, b);
-        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // D fp32, A/B bf16, both MN-major, N = 64, M = 128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                 ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      constexpr uint64_t dconst = (1ull << 46) | (2ull << 61);
-      const uint64_t a_sbo = (uint64_t)(p.sbo >> 4) << 32;
-      constexpr uint64_t b_fixed = dconst | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
-      // Everything that does not depend on the stage is folded into five 64-bit descriptor bases up front; the
-      // tile loop then issues its 5 x KSTEPS MMAs with one add each (the issuing thread's scalar latency is what
-      // bounds a loop like this -- see conv_tc_halo.cu).
-      const uint32_t ones16 = smem_u32(smem + p.ones_off) >> 4;
-      const uint32_t ks16 = (2u * p.sbo) >> 4;            // 16 pixels = two tile rows per K step
-      const uint32_t win8_16 = p.win[8] >> 4;
-      uint64_t abase[5];
+    const bool leader = elect_one();
+    // D fp32, A/B bf16, both MN-major, N = 64, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint64_t dconst = (1ull << 46) | (2ull << 61);
+    const uint64_t a_sbo = (uint64_t)(p.sbo >> 4) << 32;
+    constexpr uint64_t b_fixed = dconst | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
+    // Everything that does not depend on the stage is folded into five 64-bit descriptor bases up front; the
+    // tile loop then issues its 5 x KSTEPS MMAs with one uniform add each.
+    const uint32_t ones16 = smem_u32(smem + p.ones_off) >> 4;
+    const uint32_t ks16 = (2u * p.sbo) >> 4;            // 16 pixels = two tile rows per K step
+    const uint32_t win8_16 = p.win[8] >> 4;
+    uint64_t abase[5];
 #pragma unroll
-      for (int rb = 0; rb < 5; ++rb) {
-        const uint64_t lbo = rb < 4 ? (uint64_t)((p.win[2 * rb + 1] - p.win[2 * rb]) >> 4) << 16 : 0ull;
-        abase[rb] = dconst | a_sbo | lbo | (uint64_t)(p.win[2 * rb] >> 4);
-      }
-      int st = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[st], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + (size_t)st * p.stage_bytes);
-        const uint32_t a16 = a0 >> 4;
-        const uint64_t b_desc0 = b_fixed | (uint64_t)((a0 + (uint32_t)p.nplanes * p.slot_bytes) >> 4);
-        const uint32_t acc_on = it != 0 ? 1u : 0u;
+    for (int rb = 0; rb < 5; ++rb) {
+      const uint64_t lbo = rb < 4 ? (uint64_t)((p.win[2 * rb + 1] - p.win[2 * rb]) >> 4) << 16 : 0ull;
+      abase[rb] = dconst | a_sbo | lbo | (uint64_t)(p.win[2 * rb] >> 4);
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full_bar[st], ph);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(smem + (size_t)st * p.stage_bytes);
+      const uint32_t a16 = a0 >> 4;
+      const uint64_t b_desc0 = b_fixed | (uint64_t)((a0 + (uint32_t)p.nplanes * p.slot_bytes) >> 4);
+      const uint32_t acc_on = it != 0 ? 1u : 0u;
+      if (leader) {
 #pragma unroll
         for (int rb = 0; rb < 5; ++rb) {
 #pragma unroll
@@ -294,10 +305,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           }
         }
         umma_commit(&empty_bar[st]);
-        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
-      umma_commit(accum_bar);
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
+    if (leader) umma_commit(accum_bar);
+    __syncwarp();
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;  // accumulator row: slot half (m / 64), input channel (m % 64)

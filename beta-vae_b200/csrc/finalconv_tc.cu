@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   uint64_t* dw_full = acc_empty + 2;
   uint64_t* wt_bar = dw_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wt_bar + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -68,52 +68,59 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
   const uint32_t acc_dw = tmem_base + 128;   // columns 0..127: two dh accumulators; 128..143: dw
 
   if (warp == 0) {
-    if (lane == 0) {
+    // producer: all lanes run the loop, the elected lane issues the TMA loads (see elect_one() in tc_ptx.cuh)
+    const bool leader = elect_one();
+    if (leader) {
       if (p.wpart) tma_prefetch_desc(&maps.h);
       tma_prefetch_desc(&maps.d);
       if (p.dh) {
         mbar_expect_tx(wt_bar, 2048);
         tma_load_3d(&maps.wt, wt_bar, smem + p.wt_off, 0, 0, 0);
       }
-      int st = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-        mbar_wait(&empty_bar[st], ph ^ 1u);
-        int t = tile;
-        const int w0 = (t % p.tiles_w) * 8;
-        t /= p.tiles_w;
-        const int h0 = (t % p.tiles_h) * 16;
-        const int b = t / p.tiles_h;
-        uint8_t* base = smem + (size_t)st * FB_STAGE;
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      mbar_wait(&empty_bar[st], ph ^ 1u);
+      int t = tile;
+      const int w0 = (t % p.tiles_w) * 8;
+      t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * 16;
+      const int b = t / p.tiles_h;
+      uint8_t* base = smem + (size_t)st * FB_STAGE;
+      if (leader) {
         mbar_expect_tx(&full_bar[st], p.wpart ? FB_STAGE : FB_D_BYTES);
         if (p.wpart) tma_load_4d(&maps.h, &full_bar[st], base, 0, w0, h0, b);
         tma_load_4d(&maps.d, &full_bar[st], base + FB_H_BYTES, 0, w0, h0, b);
-        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // dh: A = D K-major (32-byte rows), B = Wt K-major (32-byte rows), N = 64
-      constexpr uint32_t idesc_dh = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      // dw: A = h MN-major SW128, B = D MN-major SW32, N = 16
-      constexpr uint32_t idesc_dw = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                    ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      constexpr uint64_t dconst = 1ull << 46;
-      constexpr uint64_t a_dw_fixed = dconst | (2ull << 61) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
-      constexpr uint64_t b_dw_fixed = dconst | (6ull << 61) | ((uint64_t)(16 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32);
-      if (p.dh) {
-        mbar_wait(wt_bar, 0);
-        tc_fence_after();
-      }
-      const uint64_t wt_desc = kmajor_desc(smem_u32(smem + p.wt_off), 32);
-      int st = 0;
-      uint32_t ph = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        mbar_wait(&full_bar[st], ph);
-        if (p.dh) mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t h_addr = smem_u32(smem + (size_t)st * FB_STAGE), d_addr = h_addr + FB_H_BYTES;
+    const bool leader = elect_one();
+    // dh: A = D K-major (32-byte rows), B = Wt K-major (32-byte rows), N = 64
+    constexpr uint32_t idesc_dh = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // dw: A = h MN-major SW128, B = D MN-major SW32, N = 16
+    constexpr uint32_t idesc_dw = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                  ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint64_t dconst = 1ull << 46;
+    constexpr uint64_t a_dw_fixed = dconst | (2ull << 61) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32);
+    constexpr uint64_t b_dw_fixed = dconst | (6ull << 61) | ((uint64_t)(16 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32);
+    if (p.dh) {
+      mbar_wait(wt_bar, 0);
+      tc_fence_after();
+    }
+    const uint64_t wt_desc = kmajor_desc(smem_u32(smem + p.wt_off), 32);
+    int st = 0;
+    uint32_t ph = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      mbar_wait(&full_bar[st], ph);
+      if (p.dh) mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t h_addr = smem_u32(smem + (size_t)st * FB_STAGE), d_addr = h_addr + FB_H_BYTES;
+      if (leader) {
         if (p.dh) {
           umma_bf16(tmem_base + buf * 64u, kmajor_desc(d_addr, 32), wt_desc, idesc_dh, 0u);
           umma_commit(&acc_full[buf]);
@@ -125,10 +132,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
                       b_dw_fixed | (uint64_t)((d_addr + k * 512u) >> 4), idesc_dw, (it | (uint32_t)k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[st]);
-        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
-      umma_commit(dw_full);
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
+    if (leader) umma_commit(dw_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;  // pixel inside the 16x8 tile

@@ -36,6 +36,20 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync).  The producer / MMA-issuer warps run their loops with all 32 lanes -- the
+// warp index comes from warp_index_uniform(), so nvcc knows the role branch and everything computed inside it is
+// warp-uniform -- and predicate only the TMA / tcgen05 instructions on the elected lane.  Descriptors and coordinates
+// then live in uniform registers and consecutive UTCHMMAs are 2-3 SASS instructions apart.  With `if (lane == 0)`
+// around the loops nvcc must assume divergence and wraps EVERY UTCHMMA / UTMALDG in an ELECT + R2UR + BRA.U.ANY
+// waterfall loop (plus uniform-register spills): measured 74-107 cycles per tcgen05.mma instead of the 48 (N = 64) /
+// 64 (N = 128) the hardware needs (profiles/umma_rate.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void tma_load_4d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"

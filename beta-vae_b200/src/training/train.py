@@ -222,6 +222,9 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
                     losses = model.loss(x, **kw)
                 losses["total"].backward()
                 engine.step()
+                # plain tensors from here on: a live autograd graph would keep this step's AccumulateGrad nodes (and
+                # their stream) alive and invalidate the next graph capture (GraphedTrainStep._body does the same)
+                losses = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in losses.items()}
             running += torch.stack([losses["total"].detach(), losses["recon"].detach(), losses["recon_base"],
                                     losses["recon_lpips"].to(device), losses["recon_ffl"].to(device),
                                     losses["kl_mean"].detach()]).float()
