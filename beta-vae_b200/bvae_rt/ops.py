@@ -189,14 +189,23 @@ def u8_to_unit_f32(src, out=None):
     return out
 
 
-def conv3x3_fprop(x, wp, bias, cout, stride, dt):
+def conv3x3_fprop(x, wp, bias, cout, stride, dt, want_stats=False):
+    """``want_stats``: also return the GroupNorm statistic partials [B, n, 2] float64 the kernel's epilogue produces
+    (None when the kernel serving this shape has no such epilogue)."""
     B, H, W, Cin = x.shape
     y = torch.empty((B, conv_out(H, stride), conv_out(W, stride), cout), dtype=torch_dtype(dt), device=x.device)
+    nparts = query("bvae_conv3x3_fprop_stats_parts", H, W, Cin, cout, stride, code_of(x), dt) if want_stats else 0
     with profiler.region(f"conv_fprop[{H}x{W}x{Cin}->{cout},s{stride}]", flops=2.0 * y.numel() * 9 * Cin,
                          nbytes=x.numel() * x.element_size() + y.numel() * y.element_size()):
-        call("bvae_conv3x3_fprop", _p(x), _p(wp), _p(bias), _p(y), B, H, W, Cin, cout, stride, code_of(x), dt,
-             _stream())
-    return y
+        if nparts > 0:
+            part = torch.empty((B, nparts, 2), dtype=torch.float64, device=x.device)
+            call("bvae_conv3x3_fprop_stats", _p(x), _p(wp), _p(bias), _p(y), _p(part), B, H, W, Cin, cout, stride,
+                 code_of(x), dt, _stream())
+        else:
+            part = None
+            call("bvae_conv3x3_fprop", _p(x), _p(wp), _p(bias), _p(y), B, H, W, Cin, cout, stride, code_of(x), dt,
+                 _stream())
+    return (y, part) if want_stats else y
 
 
 def conv3x3_dgrad(dy, wpt, in_shape, stride):
@@ -272,25 +281,38 @@ def upsample2x_bwd(dy):
     return dx
 
 
-def gn_relu_se_fwd(y, gamma, beta, w1, b1, w2, b2):
+def gn_relu_se_fwd(y, gamma, beta, w1, b1, w2, b2, up=False, stat_part=None):
+    """GroupNorm(1,C) + ReLU + SE.  ``up``: return the bilinear x2 upsample of the activation ([B,2H,2W,C]) without
+    materialising it at its own resolution.  ``stat_part``: [B, n, 2] float64 partial (sum, sum of squares) of ``y``
+    from the convolution's epilogue (skips the statistics pass)."""
     B, H, W, Cc = y.shape
     P = H * W
     dev = y.device
     has_se = w1 is not None
     R = w1.shape[0] if has_se else 0
-    out = torch.empty_like(y)
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=y.dtype, device=dev) if up else torch.empty_like(y)
     stats = torch.empty((B, 2), dtype=torch.float32, device=dev)
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     cpos, spos, hidden, gate = (f(B, Cc), f(B, Cc), f(B, R), f(B, Cc)) if has_se else (None,) * 4
-    ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
+    nsp = 0 if stat_part is None else stat_part.shape[1]
     # algorithmic bytes: one read of y + one write of out (SURVEY.md 8d)
-    with profiler.region(f"gn_relu_se_fwd[{H}x{W}x{Cc}]", nbytes=2.0 * y.numel() * y.element_size()):
-        call("bvae_gn_relu_se_fwd", _p(y), _p(out), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P, Cc, R,
-             _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(ws), ws.numel(), code_of(y), _stream())
+    if up:
+        ws = _ws(query("bvae_gn_relu_se_up_workspace", B, H, W, Cc), dev)
+        with profiler.region(f"gn_relu_se_up_fwd[{H}x{W}x{Cc}]", nbytes=(y.numel() + out.numel()) * y.element_size()):
+            call("bvae_gn_relu_se_up_fwd", _p(y), _p(out), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, H, W,
+                 Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(stat_part), nsp, _p(ws), ws.numel(),
+                 code_of(y), _stream())
+    else:
+        ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
+        with profiler.region(f"gn_relu_se_fwd[{H}x{W}x{Cc}]", nbytes=2.0 * y.numel() * y.element_size()):
+            call("bvae_gn_relu_se_fwd", _p(y), _p(out), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B, P, Cc, R,
+                 _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(stat_part), nsp, _p(ws), ws.numel(),
+                 code_of(y), _stream())
     return out, (stats, cpos, spos, hidden, gate)
 
 
-def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved):
+def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved, up=False):
+    """``up``: ``dout`` is the gradient w.r.t. the upsampled activation, [B,2H,2W,C]."""
     B, H, W, Cc = y.shape
     P = H * W
     dev = y.device
@@ -300,6 +322,14 @@ def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved):
     dy = torch.empty_like(y)
     dgamma, dbeta = grad_out(gamma), grad_out(beta)
     dw1, db1, dw2, db2 = (grad_out(w1), grad_out(b1), grad_out(w2), grad_out(b2)) if has_se else (None,) * 4
+    if up:
+        assert tuple(dout.shape) == (B, 2 * H, 2 * W, Cc), (dout.shape, y.shape)
+        ws = _ws(query("bvae_gn_relu_se_up_workspace", B, H, W, Cc), dev)
+        with profiler.region(f"gn_relu_se_up_bwd[{H}x{W}x{Cc}]", nbytes=(dout.numel() + 2.0 * y.numel()) * y.element_size()):
+            call("bvae_gn_relu_se_up_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B,
+                 H, W, Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1),
+                 _p(db1), _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
+        return dy, dgamma, dbeta, dw1, db1, dw2, db2
     ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
     # algorithmic bytes: read dout + read y + write dy
     with profiler.region(f"gn_relu_se_bwd[{H}x{W}x{Cc}]", nbytes=3.0 * y.numel() * y.element_size()):
@@ -312,16 +342,32 @@ def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved):
 # --------------------------------------------------------------------------------------
 # autograd Functions
 # --------------------------------------------------------------------------------------
-class ConvGnSeBlock(torch.autograd.Function):
-    """[bilinear x2 ->] conv3x3 -> GroupNorm(1,C) -> ReLU -> [SE]: one encoder ConvBlock or
-    decoder DeconvBlock of the reference (src/models/beta_vae.py:33-66)."""
+class Upsample2x(torch.autograd.Function):
+    """nn.Upsample(x2, bilinear, align_corners=False) on NHWC (reference: src/models/beta_vae.py:52-53) -- the stand-alone
+    form, used in front of the first decoder block; between decoder blocks the upsample is fused into ConvGnSeBlock."""
 
     @staticmethod
-    def forward(ctx, x, cw, cb, gw, gb, w1, b1, w2, b2, packs, key, stride, upsample, dt):
-        xin = upsample2x_fwd(x) if upsample else x
-        _, H, W, Cin = xin.shape
+    def forward(ctx, x):
+        return upsample2x_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return upsample2x_bwd(dy.contiguous())
+
+
+class ConvGnSeBlock(torch.autograd.Function):
+    """conv3x3 -> GroupNorm(1,C) -> ReLU -> [SE] [-> bilinear x2]: one encoder ConvBlock or decoder DeconvBlock of the
+    reference (src/models/beta_vae.py:33-66).  A decoder block's nn.Upsample belongs to its INPUT in the reference;
+    here it is produced by the block in front (``up_after``), fused into that block's normalise / rescale pass, so the
+    activation is written once, already upsampled, and the backward's transposed stencil is fused into the
+    GroupNorm-backward reduction pass."""
+
+    @staticmethod
+    def forward(ctx, x, cw, cb, gw, gb, w1, b1, w2, b2, packs, key, stride, up_after, dt):
+        _, H, W, Cin = x.shape
         Cout = cw.shape[0]
-        first_tc = ((not upsample) and xin.dtype == torch.float32 and not x.requires_grad and
+        xin = x
+        first_tc = (xin.dtype == torch.float32 and not x.requires_grad and
                     conv_first_supported(H, W, Cin, Cout, stride, dt))
         if first_tc:
             # first encoder layer: 9-tap im2col of the image + one tcgen05 MMA per tile; xcol replaces x for the backward
@@ -333,20 +379,35 @@ class ConvGnSeBlock(torch.autograd.Function):
             lb = conv_weight_layout(H, W, Cin, Cout, stride, dt, 1)
             wp = packs.get(f"{key}.fprop.{lf}", (cw,), dt, lambda: pack_conv(cw, dt, False, lf))
             wpt = packs.get(f"{key}.dgrad.{lb}", (cw,), dt, lambda: pack_conv(cw, dt, True, lb))
-            y = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt)
-        out, saved = gn_relu_se_fwd(y, gw, gb, w1, b1, w2, b2)
+            Ho, Wo = conv_out(H, stride), conv_out(W, stride)
+            streaming = not query("bvae_gn_relu_se_prefers_unfused", x.shape[0], Ho * Wo, Cout,
+                                  w1.shape[0] if w1 is not None else 0, dt)
+            # where the streaming GroupNorm passes run, the conv's epilogue delivers their statistics
+            y, stat_part = conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt, want_stats=True) if streaming else \
+                (conv3x3_fprop(xin, wp, cb, cw.shape[0], stride, dt), None)
+        if first_tc:
+            stat_part = None
+        # fuse the next block's bilinear x2 only where the streaming GroupNorm passes run anyway; shapes served by the
+        # single-launch cluster kernel keep the upsample as its own pass (measured faster, see gn_se.cu)
+        Bn, Ho, Wo, _ = y.shape
+        fuse_up = bool(up_after) and not query("bvae_gn_relu_se_prefers_unfused", Bn, Ho * Wo, Cout,
+                                                 w1.shape[0] if w1 is not None else 0, code_of(y))
+        out, saved = gn_relu_se_fwd(y, gw, gb, w1, b1, w2, b2, up=fuse_up, stat_part=stat_part)
+        if up_after and not fuse_up:
+            out = upsample2x_fwd(out)
         stats, cpos, spos, hidden, gate = saved
         ctx.save_for_backward(xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate, cw, cb)
-        ctx.stride, ctx.upsample, ctx.first_tc = stride, upsample, first_tc
-        ctx.in_shape = (x.shape[0], H, W, Cin)
+        ctx.stride, ctx.up_after, ctx.fuse_up, ctx.first_tc = stride, up_after, fuse_up, first_tc
         return out
 
     @staticmethod
     def backward(ctx, dout):
         xin, y, gw, gb, w1, b1, w2, b2, wpt, stats, cpos, spos, hidden, gate, cw, cb = ctx.saved_tensors
         dout = dout.contiguous()
+        if ctx.up_after and not ctx.fuse_up:
+            dout = upsample2x_bwd(dout)
         dy, dgw, dgb, dw1, db1, dw2, db2 = gn_relu_se_bwd(dout, y, gw, gb, w1, b1, w2, b2,
-                                                          (stats, cpos, spos, hidden, gate))
+                                                          (stats, cpos, spos, hidden, gate), up=ctx.fuse_up)
         if ctx.first_tc:
             if ctx.needs_input_grad[0]:
                 raise lib.BvaeError("the tcgen05 first-layer path does not produce an input gradient")
@@ -356,8 +417,6 @@ class ConvGnSeBlock(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = conv3x3_dgrad(dy, wpt, tuple(xin.shape), ctx.stride)
-            if ctx.upsample:
-                dx = upsample2x_bwd(dx)
         return dx, dcw, dcb, dgw, dgb, dw1, db1, dw2, db2, None, None, None, None, None
 
 

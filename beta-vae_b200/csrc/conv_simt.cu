@@ -615,6 +615,24 @@ extern "C" int bvae_conv3x3_weight_layout(int H, int W, int Cin, int Cout, int s
   return conv_tc_supported(H, W, Cin, Cout, stride, kind) ? 1 : 0;
 }
 
+/* Number of per-sample (sum, sum of squares) partials bvae_conv3x3_fprop_stats writes for this shape; 0 = the kernel
+ * that serves the shape has no statistics epilogue (run the fprop without it). */
+extern "C" int bvae_conv3x3_fprop_stats_parts(int H, int W, int Cin, int Cout, int stride, int x_dtype, int y_dtype) {
+  if (stride != 1 || x_dtype != BVAE_BF16 || y_dtype != BVAE_BF16) return 0;
+  if (bvae_conv3x3_weight_layout(H, W, Cin, Cout, stride, BVAE_BF16, 0) != 1) return 0;
+  if (!conv_halo_supported(H, W, Cin, Cout)) return 0;
+  return conv_halo_stat_parts(H, W, Cout);
+}
+
+extern "C" int bvae_conv3x3_fprop_stats(const void* x, const void* wp, const float* bias, void* y, double* stat_part, int B,
+                                        int H, int W, int Cin, int Cout, int stride, int x_dtype, int y_dtype,
+                                        bvae_stream_t stream) {
+  BVAE_REQUIRE(x && wp && y && stat_part, BVAE_ERR_ARG, "conv3x3_fprop_stats: null pointer");
+  BVAE_REQUIRE(bvae_conv3x3_fprop_stats_parts(H, W, Cin, Cout, stride, x_dtype, y_dtype) > 0, BVAE_ERR_UNSUPPORTED,
+               "conv3x3_fprop_stats: no statistics epilogue for this shape");
+  return conv_tc_fprop(x, wp, bias, y, B, H, W, Cin, Cout, stride, as_stream(stream), stat_part);
+}
+
 extern "C" int bvae_conv3x3_fprop(const void* x, const void* wp, const float* bias, void* y, int B, int H, int W,
                                   int Cin, int Cout, int stride, int x_dtype, int y_dtype, bvae_stream_t stream) {
   BVAE_REQUIRE(x && wp && y, BVAE_ERR_ARG, "conv3x3_fprop: null pointer");

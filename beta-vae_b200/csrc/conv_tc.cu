@@ -227,8 +227,10 @@ static int make_weight_map(CUtensorMap* m, const void* wp, int K, int N, int kc,
 }
 
 int conv_tc_fprop(const void* x, const void* wp, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
-                  int stride, cudaStream_t st) {
-  if (stride == 1 && conv_halo_supported(H, W, Cin, Cout)) return conv_halo_launch(x, wp, bias, y, B, H, W, Cin, Cout, 0, st);
+                  int stride, cudaStream_t st, double* stat_part) {
+  if (stride == 1 && conv_halo_supported(H, W, Cin, Cout))
+    return conv_halo_launch(x, wp, bias, y, B, H, W, Cin, Cout, 0, st, stat_part);
+  BVAE_REQUIRE(stat_part == nullptr, BVAE_ERR_UNSUPPORTED, "conv_tc_fprop: statistics output needs the stride-1 halo kernel");
   TcMaps maps;
   TcParams p;
   memset(&p, 0, sizeof(p));

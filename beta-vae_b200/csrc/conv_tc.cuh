@@ -38,14 +38,16 @@ struct TcParams {
 // kind 0 = fprop, 1 = dgrad.  True when the tcgen05 kernel covers the shape (bf16 only).
 bool conv_tc_supported(int H, int W, int Cin, int Cout, int stride, int kind);
 int conv_tc_fprop(const void* x, const void* wp_nk, const float* bias, void* y, int B, int H, int W, int Cin,
-                  int Cout, int stride, cudaStream_t st);
+                  int Cout, int stride, cudaStream_t st, double* stat_part = nullptr);
 int conv_tc_dgrad(const void* dy, const void* wpt_nk, void* dx, int B, int H, int W, int Cin, int Cout, int stride,
                   cudaStream_t st);
 
 // ---- stride-1 halo kernel (conv_tc_halo.cu): persistent, one shared-memory halo per tile, weights resident ----
 bool conv_halo_supported(int H, int W, int K, int N);
+// stat_part (optional): [B][conv_halo_stat_parts(H, W, N)][2] doubles, per-sample partial (sum, sum of squares) of dst
 int conv_halo_launch(const void* src, const void* wp_nk, const float* bias, void* dst, int B, int H, int W, int K, int N,
-                     int dgrad, cudaStream_t st);
+                     int dgrad, cudaStream_t st, double* stat_part = nullptr);
+int conv_halo_stat_parts(int H, int W, int N);
 
 bool conv_halo_final_supported(int H, int W, int C, int Co);
 int conv_halo_final_rows(int Co);   // rows of the [rows][C] weight pack (9 * Co padded to the UMMA N)

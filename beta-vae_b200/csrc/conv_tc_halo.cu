@@ -51,13 +51,17 @@ struct HaloParams {
   int nbuf, tmem_cols;     // accumulator buffers in TMEM
   int dbg;                 // BVAE_HALO_DBG ablation bits (dev): 1 no global stores, 2 no epilogue work, 4 no MMAs, 8 no halo TMA
   uint32_t a_off, b_off, bar_off;
+  uint32_t c_off;          // output staging: cst buffers of [128 px][64 ch] bf16 (SWIZZLE_128B), stored by TMA
+  int cst;
   __nv_bfloat16* dst;
   const float* bias;
+  double* stat_part;       // optional [B][tiles per sample * N/64 * 4][2]: per-warp (sum, sum of squares) of the stored output
 };
 
 struct HaloMaps {
   CUtensorMap x;
   CUtensorMap w;
+  CUtensorMap y;           // dst [B][H][W][N], box 64 ch x 8 x 16 pixels
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -254,10 +258,14 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // TMEM -> registers -> (+bias, bf16) -> 128B-swizzled staging tile in shared memory -> ONE TMA store per 64-channel
+    // block.  (Storing straight from registers -- 16 bytes per lane, every lane in another 128-byte line -- costs 32
+    // LSU wavefronts per instruction: ~2000 cycles per tile, more than the tile's MMAs.)
     const int q = warp & 3;
-    const int r = q * 32 + lane;            // pixel inside the 16x8 tile
-    const int hl = r / HL_TW, wl = r % HL_TW;
-    uint32_t iu = 0;
+    const int r = q * 32 + lane;            // pixel inside the 16x8 tile = row of the staging tile
+    const bool store_leader = (warp == 2) && elect_one();
+    uint8_t* stage0 = smem + p.c_off;
+    uint32_t iu = 0, is = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const int nt = u % p.n_tiles, mg = u / p.n_tiles;
       const int n0 = nt * BN;
@@ -272,15 +280,24 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
         const int h0 = (mt % p.tiles_h) * HL_TH;
         const int b = mt / p.tiles_h;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.tm * BN) + (uint32_t)(m * BN);
-        {
-          __nv_bfloat16* out = p.dst + (((size_t)b * p.H + (size_t)(h0 + hl)) * p.W + (size_t)(w0 + wl)) * p.N + n0;
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
-            if (p.dbg & 2) break;
+        for (int cb = 0; cb < BN; cb += 64, ++is) {
+          if (p.dbg & 2) break;
+          uint8_t* stg = stage0 + (size_t)(is % (uint32_t)p.cst) * 16384u;
+          // the TMA store that last read this staging buffer must be done with it
+          if (store_leader) {
+            if (p.cst == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          named_bar_sync(1, 128);
+          uint8_t* row = stg + (size_t)r * 128u;
+          float st_s = 0.f, st_q = 0.f;     // GroupNorm statistics of what is stored (bf16-rounded), for the next pass
+#pragma unroll
+          for (int c = 0; c < 64; c += 32) {
             uint32_t v[32];
-            tmem_ld32(taddr + (uint32_t)c, v);
+            tmem_ld32(taddr + (uint32_t)(cb + c), v);
             tmem_ld_wait();
-            const float4* bq = reinterpret_cast<const float4*>(bias_sm + n0 + c);
+            const float4* bq = reinterpret_cast<const float4*>(bias_sm + n0 + cb + c);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const float4 b0 = bq[2 * g], b1 = bq[2 * g + 1];
@@ -292,10 +309,30 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
                 const float f1 = __uint_as_float(v[g * 8 + 2 * e + 1]) + bb[2 * e + 1];
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
                 pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                const float r0 = __uint_as_float(pk[e] << 16), r1 = __uint_as_float(pk[e] & 0xffff0000u);
+                st_s += r0 + r1;
+                st_q = fmaf(r0, r0, fmaf(r1, r1, st_q));
               }
-              if (!(p.dbg & 1) || pk[0] == 0x12345678u)
-                *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              const uint32_t chunk = (uint32_t)(c / 8 + g);     // 16-byte chunk of the 128-byte row, XOR-swizzled by the row
+              *reinterpret_cast<uint4*>(row + ((chunk ^ (uint32_t)(r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+          }
+          if (p.stat_part) {
+            st_s = warp_sum(st_s);
+            st_q = warp_sum(st_q);
+            if (lane == 0) {
+              const int tps = p.tiles_w * p.tiles_h;                 // tiles per sample
+              const int ts = (mg * p.tm + m) - b * tps;
+              const size_t slot = ((size_t)b * tps + ts) * (size_t)(p.N / 64) + (size_t)((n0 + cb) / 64);
+              p.stat_part[(slot * 4 + q) * 2] = (double)st_s;
+              p.stat_part[(slot * 4 + q) * 2 + 1] = (double)st_q;
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (store_leader && !(p.dbg & 1)) {
+            tma_store_4d(&maps.y, stg, n0 + cb, w0, h0, b);
+            tma_store_commit();
           }
         }
       }
@@ -303,6 +340,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (store_leader) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -319,11 +357,14 @@ bool conv_halo_supported(int H, int W, int K, int N) {
   return H % HL_TH == 0 && W % HL_TW == 0 && K % 64 == 0 && N % 64 == 0 && (N <= 256 ? (N & (N - 1)) == 0 : N % 256 == 0);
 }
 
+int conv_halo_stat_parts(int H, int W, int N) { return (H / HL_TH) * (W / HL_TW) * (N / 64) * 4; }
+
 int conv_halo_launch(const void* src, const void* wp, const float* bias, void* dst, int B, int H, int W, int K, int N,
-                     int dgrad, cudaStream_t st) {
+                     int dgrad, cudaStream_t st, double* stat_part) {
   HaloMaps maps;
   HaloParams p;
   memset(&p, 0, sizeof(p));
+  p.stat_part = stat_part;
   p.dgrad = dgrad ? 1 : 0;
   if (const char* e = getenv("BVAE_HALO_DBG")) p.dbg = atoi(e);
   p.kchunks = K / 64;
@@ -335,11 +376,12 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
   p.bias = bias;
   const int sms = num_sms();
   const size_t bar_bytes = 256 + (size_t)N * sizeof(float) + 64;  // mbarriers + bias[N]
-  // resident weights: the whole [9][bn][K] slab plus at least two halo slots must fit
+  // resident weights: the whole [9][bn][K] slab plus at least two halo slots and one output staging tile must fit
+  constexpr size_t STG = 16384;   // [128 px][64 ch] bf16
   int bn_res = 0;
   for (int bn = (N < 256 ? N : 256); bn >= 64; bn >>= 1) {
     if (N % bn) continue;
-    if ((size_t)9 * K * bn * 2 + 2 * HL_HALO_SLOT + bar_bytes + 1024 <= HL_SMEM_MAX) {
+    if ((size_t)9 * K * bn * 2 + 2 * HL_HALO_SLOT + STG + bar_bytes + 1024 <= HL_SMEM_MAX) {
       bn_res = bn;
       break;
     }
@@ -351,11 +393,17 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
     p.tm = 1;
     p.sb = 0;
     const size_t wbytes = (size_t)9 * K * p.bn * 2;
-    int sa = (int)((HL_SMEM_MAX - 1024 - bar_bytes - wbytes) / HL_HALO_SLOT);
-    p.sa = sa > 4 ? 4 : sa;
+    // halo slots first: the kernel is bound by bytes in flight per SM (Little's law: ~2.4 us load latency under load),
+    // so every spare 24 KB goes to the input ring; the output staging is double-buffered only if room is left
+    const size_t room = HL_SMEM_MAX - 1024 - bar_bytes - wbytes;
+    int sa = (int)((room - STG) / HL_HALO_SLOT);
+    p.sa = sa > 6 ? 6 : sa;
+    if (const char* e = getenv("BVAE_HALO_SA")) p.sa = atoi(e) < p.sa ? atoi(e) : p.sa;
+    p.cst = (room - (size_t)p.sa * HL_HALO_SLOT) >= 2 * STG ? 2 : 1;
     p.b_off = 0;
     p.a_off = (uint32_t)wbytes;  // multiple of 1024 (bn*128*9*kchunks)
-    p.bar_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;
+    p.c_off = p.a_off + (uint32_t)p.sa * HL_HALO_SLOT;
+    p.bar_off = p.c_off + (uint32_t)(p.cst * STG);
     smem = 1024 + p.bar_off + bar_bytes;
   } else {
     p.resident = 0;
@@ -363,12 +411,14 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
     const int units1 = p.m_tiles * (N / p.bn);
     p.tm = (units1 / 2 >= (sms * 4) / 5) ? 2 : 1;
     p.sa = p.tm == 2 ? 2 : 3;
+    p.cst = 2;
     const size_t a_bytes = (size_t)p.sa * p.tm * HL_HALO_SLOT;
-    int sb = (int)((HL_SMEM_MAX - 1024 - bar_bytes - a_bytes) / ((size_t)p.bn * HL_ROW));
+    int sb = (int)((HL_SMEM_MAX - 1024 - bar_bytes - a_bytes - p.cst * STG) / ((size_t)p.bn * HL_ROW));
     p.sb = sb > 8 ? 8 : sb;
     p.a_off = 0;
     p.b_off = (uint32_t)a_bytes;
-    p.bar_off = p.b_off + (uint32_t)p.sb * p.bn * HL_ROW;
+    p.c_off = p.b_off + (uint32_t)p.sb * p.bn * HL_ROW;
+    p.bar_off = p.c_off + (uint32_t)(p.cst * STG);
     smem = 1024 + p.bar_off + bar_bytes;
   }
   p.n_tiles = N / p.bn;
@@ -392,6 +442,13 @@ int conv_halo_launch(const void* src, const void* wp, const float* bias, void* d
     const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * N * 2};
     const uint32_t box[3] = {64u, (uint32_t)p.bn, 1u};
     int rc = make_map(&maps.w, wp, 3, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)N * 2, (uint64_t)W * N * 2, (uint64_t)H * W * N * 2};
+    const uint32_t box[4] = {64u, (uint32_t)HL_TW, (uint32_t)HL_TH, 1u};
+    int rc = make_map(&maps.y, dst, 4, dims, strides, box, 128);
     if (rc) return rc;
   }
   int grid = p.units < sms ? p.units : sms;

@@ -17,4 +17,7 @@ int gn_cluster_bwd(const T* dout, const T* y, T* dy, const float* gamma, const f
                    const float* hidden, const float* gate, float* G1, float* G2, float* dz2, float* dz1, cudaStream_t st,
                    bool* handled);
 
+// true when the cluster-resident forward kernel covers the shape (element size 2 or 4 bytes)
+bool gn_cluster_eligible(int B, int P, int C, int R, int elem_bytes);
+
 }  // namespace bvae

@@ -32,24 +32,43 @@ struct GnGeom {
   int nchunks;
 };
 
-static inline int gn_pixels_per_chunk(int P, int C) {
-  int pc = 32768 / (C > 0 ? C : 1);
-  if (pc < 8) pc = 8;
+// Pixels per chunk (= per CTA).  The passes are pure streaming, so what matters is bytes in flight: enough CTAs to
+// fill every SM several times over (>= ~4 per SM when the tensor allows it) and at most 16 vectors per thread.  The
+// round-1 rule (a fixed 64 KB per CTA) left the small deep layers with 32 CTAs on 148 SMs.
+static inline int gn_pixels_per_chunk(int B, int P, int C, int rows) {
+  if (rows < 1) rows = 1;
+  const long long want = 4LL * num_sms();                 // CTAs
+  long long nch = (want + B - 1) / (B > 0 ? B : 1);
+  if (nch < 1) nch = 1;
+  long long pc = (P + nch - 1) / nch;
+  pc = (pc + rows - 1) / rows * rows;                      // whole rounds of the CTA's pixel rows
+  if (pc < rows) pc = rows;
+  if (pc > 16LL * rows) pc = 16LL * rows;
+  const long long floor_pc = (32768 / (C > 0 ? C : 1)) / 64;   // never below ~1 KB per CTA
+  if (pc < floor_pc) pc = floor_pc;
   if (pc > P) pc = P;
-  return pc;
+  return (int)pc;
 }
-static inline int gn_num_chunks(int P, int C) { return cdiv(P, gn_pixels_per_chunk(P, C)); }
 
-static inline bool gn_geom(int P, int C, int vec, GnGeom* g) {
+static inline bool gn_geom(int B, int P, int C, int vec, GnGeom* g) {
   if (C % vec != 0) return false;
   g->cv = C / vec;
   if (g->cv > kGnThreads) return false;
   g->rows = kGnThreads / g->cv;
   if (g->rows < 1) g->rows = 1;
   g->threads = (g->cv * g->rows + 31) / 32 * 32;  // whole warps; surplus threads idle (row >= rows)
-  g->pc = gn_pixels_per_chunk(P, C);
+  g->pc = gn_pixels_per_chunk(B, P, C, g->rows);
   g->nchunks = cdiv(P, g->pc);
   return true;
+}
+// upper bound of the chunk count over both element types (workspace sizing does not know the dtype)
+static inline int gn_max_chunks(int B, int P, int C) {
+  int n = 1;
+  for (int vec : {4, 8}) {
+    GnGeom g;
+    if (gn_geom(B, P, C, vec, &g) && g.nchunks > n) n = g.nchunks;
+  }
+  return n;
 }
 
 // Every CTA re-derives (mean, rstd) of its sample from the stats partials: nchunks doubles.
@@ -101,7 +120,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const T* __restric
 // ------------------------------------------------------------------ forward: pooled sums over positive pixels
 template <typename T>
 __global__ void __launch_bounds__(kGnThreads)
-    gn_pool_kernel(const T* __restrict__ y, const double* __restrict__ spart, const float* __restrict__ gamma,
+    gn_pool_kernel(const T* __restrict__ y, const double* __restrict__ spart, int nsp, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ cpart, float* __restrict__ xpart,
                    float* __restrict__ stats, int P, int C, int cv, int rows, int pc) {
   constexpr int V = Vec16<T>::N;
@@ -109,7 +128,7 @@ __global__ void __launch_bounds__(kGnThreads)
   __shared__ double red[32];
   const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   float mean, rstd;
-  sample_stats(spart + (size_t)b * nchunks * 2, nchunks, (double)P * C, &mean, &rstd, red);
+  sample_stats(spart + (size_t)b * nsp * 2, nsp, (double)P * C, &mean, &rstd, red);
   if (chunk == 0 && threadIdx.x == 0) {
     stats[2 * b] = mean;
     stats[2 * b + 1] = rstd;
@@ -163,8 +182,34 @@ __global__ void __launch_bounds__(kGnThreads)
   }
 }
 
-// ------------------------------------------------------------------ forward: excitation (one CTA per sample)
+// ------------------------------------------------------------------ forward: (mean, rstd) from the partials, blocks without SE
+// one warp per sample
 __global__ void __launch_bounds__(256)
+    gn_finalize_stats_kernel(const double* __restrict__ spart, int nsp, double count, float* __restrict__ stats, int B) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  double s = 0.0, ss = 0.0;
+  for (int i = lane; i < nsp; i += 32) {
+    s += spart[((size_t)b * nsp + i) * 2];
+    ss += spart[((size_t)b * nsp + i) * 2 + 1];
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * b] = (float)mean;
+    stats[2 * b + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+  }
+}
+
+// ------------------------------------------------------------------ forward: excitation (one CTA per sample)
+// Latency is what this kernel costs (one CTA per sample, everything else waits for the gate): every phase is written as
+// ONE batch of independent loads per thread -- chunk partials, W1 rows (a warp per hidden unit, 16-byte lane loads), W2
+// rows (a thread per channel, 16-byte loads) -- instead of load-use chains.
+static constexpr int kExThreads = 512;
+__global__ void __launch_bounds__(kExThreads)
     se_excite_kernel(const float* __restrict__ cpart, const float* __restrict__ xpart, int nchunks,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ w1,
                      const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
@@ -174,9 +219,8 @@ __global__ void __launch_bounds__(256)
   float* pool = sm;
   float* hid = sm + C;
   const int b = blockIdx.x;
-  __shared__ double cs0[256], cs1[256];
-  // chunk sums: thread (c, g) adds chunks g, g+G, ... (G = blockDim / C thread groups when C is small), then a
-  // fixed-order combine -- a single thread per channel walking all chunks is latency bound
+  __shared__ double cs0[kExThreads], cs1[kExThreads];
+  // chunk sums: thread (c, g) adds chunks g, g+G, ... (G thread groups when C is small), then a fixed-order combine
   const int G = (C < (int)blockDim.x) ? (int)blockDim.x / C : 1;
   for (int c0 = 0; c0 < C; c0 += blockDim.x) {
     const int c = (G > 1) ? (int)threadIdx.x % C : c0 + (int)threadIdx.x;
@@ -188,10 +232,16 @@ __global__ void __launch_bounds__(256)
       double av[4] = {0.0, 0.0, 0.0, 0.0}, qv[4] = {0.0, 0.0, 0.0, 0.0};
       int k = g;
       for (; k + 3 * G < nchunks; k += 4 * G) {
+        float cf[4], xf[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          av[u] += (double)cp[(size_t)(k + u * G) * C];
-          qv[u] += (double)xp[(size_t)(k + u * G) * C];
+          cf[u] = cp[(size_t)(k + u * G) * C];
+          xf[u] = xp[(size_t)(k + u * G) * C];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          av[u] += (double)cf[u];
+          qv[u] += (double)xf[u];
         }
       }
       for (; k < nchunks; k += G) {
@@ -223,8 +273,23 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int j = warp; j < R; j += nwarp) {  // warp-shuffle mat-vec: hidden = relu(W1 pool + b1)
+    const float* wr = w1 + (size_t)j * C;
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], pool[c], acc);
+    if ((C & 127) == 0) {              // 16-byte lane loads, all of the row's loads in flight at once
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 wv = *reinterpret_cast<const float4*>(wr + c);
+        const float4 pv = *reinterpret_cast<const float4*>(pool + c);
+        a4[0] = fmaf(wv.x, pv.x, a4[0]);
+        a4[1] = fmaf(wv.y, pv.y, a4[1]);
+        a4[2] = fmaf(wv.z, pv.z, a4[2]);
+        a4[3] = fmaf(wv.w, pv.w, a4[3]);
+      }
+      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    } else {
+      for (int c = lane; c < C; c += 32) acc = fmaf(wr[c], pool[c], acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0) {
       const float h = fmaxf(acc + b1[j], 0.f);
@@ -236,8 +301,23 @@ __global__ void __launch_bounds__(256)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {  // gate = sigmoid(W2 hidden + b2)
     float acc = b2[c];
     const float* wr = w2 + (size_t)c * R;
+    if ((R & 3) == 0) {
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4* wq = reinterpret_cast<const float4*>(wr);
+      const float4* hq = reinterpret_cast<const float4*>(hid);
 #pragma unroll 8
-    for (int j = 0; j < R; ++j) acc = fmaf(wr[j], hid[j], acc);
+      for (int j = 0; j < R / 4; ++j) {
+        const float4 w4 = wq[j], h4 = hq[j];
+        a4[0] = fmaf(w4.x, h4.x, a4[0]);
+        a4[1] = fmaf(w4.y, h4.y, a4[1]);
+        a4[2] = fmaf(w4.z, h4.z, a4[2]);
+        a4[3] = fmaf(w4.w, h4.w, a4[3]);
+      }
+      acc += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < R; ++j) acc = fmaf(wr[j], hid[j], acc);
+    }
     gate[(size_t)b * C + c] = 1.0f / (1.0f + expf(-acc));
   }
 }
@@ -245,18 +325,12 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------ forward: normalise + relu + rescale
 template <typename T>
 __global__ void __launch_bounds__(kGnThreads)
-    gn_scale_kernel(const T* __restrict__ y, T* __restrict__ out, const double* __restrict__ spart,
+    gn_scale_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ gate,
-                    float* __restrict__ stats, int P, int C, int cv, int rows, int pc) {
+                    int P, int C, int cv, int rows, int pc) {
   constexpr int V = Vec16<T>::N;
-  __shared__ double red[32];
-  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  float mean, rstd;
-  sample_stats(spart + (size_t)b * nchunks * 2, nchunks, (double)P * C, &mean, &rstd, red);
-  if (chunk == 0 && threadIdx.x == 0) {
-    stats[2 * b] = mean;
-    stats[2 * b + 1] = rstd;
-  }
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const float mean = stats[2 * b], rstd = stats[2 * b + 1];   // written by the pool pass / gn_finalize_stats_kernel
   const int col = threadIdx.x % cv, row = threadIdx.x / cv;
   const int p0 = chunk * pc, p1 = min(P, p0 + pc);
   float zs[V], bs_[V];   // gate folded in: relu(z) * s = max(z * s, 0) for the sigmoid gate s > 0
@@ -343,7 +417,7 @@ __global__ void __launch_bounds__(kGnThreads)
 //   G1      = s*A1 + dpool/P * cpos    (= sum_p g,       g = d relu-input)
 //   G2      = s*A2 + dpool/P * spos    (= sum_p g*xhat)
 //   S1, S2  = sum_c gamma*G1, sum_c gamma*G2          (GroupNorm backward sums)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kExThreads)
     gn_bwd_mid_kernel(const float* __restrict__ a1part, const float* __restrict__ a2part, int nchunks,
                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ w1,
                       const float* __restrict__ w2, const float* __restrict__ cpos, const float* __restrict__ spos,
@@ -358,7 +432,7 @@ __global__ void __launch_bounds__(256)
   float* dz1 = sm + 3 * C;
   const int b = blockIdx.x;
   const bool has_se = (w1 != nullptr);
-  __shared__ double cs0[256], cs1[256];
+  __shared__ double cs0[kExThreads], cs1[kExThreads];
   const int G = (C < (int)blockDim.x) ? (int)blockDim.x / C : 1;   // thread groups sharing the chunk loop (see se_excite_kernel)
   for (int c0 = 0; c0 < C; c0 += blockDim.x) {
     const int c = (G > 1) ? (int)threadIdx.x % C : c0 + (int)threadIdx.x;
@@ -399,9 +473,9 @@ __global__ void __launch_bounds__(256)
       A1[c] = a;
       A2[c] = q;
       if (has_se) {
-        const float s = gate[(size_t)b * C + c];
-        const float ds = gamma[c] * q + beta[c] * a;
-        const float t = ds * s * (1.f - s);
+        const double s = (double)gate[(size_t)b * C + c];
+        const double ds = (double)gamma[c] * qd + (double)beta[c] * ad;   // the two terms cancel: keep the double sums
+        const float t = (float)(ds * s * (1.0 - s));
         dz2[c] = t;
         dz2o[(size_t)b * C + c] = t;
       }
@@ -409,17 +483,33 @@ __global__ void __launch_bounds__(256)
     if (G > 1) break;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (has_se) {
-    for (int j = warp; j < R; j += nwarp) {  // dh[j] = sum_c dz2[c] * W2[c][j]
-      float acc = 0.f;
-      for (int c = lane; c < C; c += 32) acc = fmaf(dz2[c], w2[(size_t)c * R + j], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        const float t = hidden[(size_t)b * R + j] > 0.f ? acc : 0.f;
-        dz1[j] = t;
-        dz1o[(size_t)b * R + j] = t;
+    // dh[j] = sum_c dz2[c] * W2[c][j].  W2 is [C][R]: threads run along j (coalesced rows), channel groups in
+    // parallel, eight independent loads per trip; the group partials are combined in double (signed terms cancel).
+    const int ng = max(1, (int)blockDim.x / R);
+    const int jj = threadIdx.x % R, cgp = threadIdx.x / R;
+    float part = 0.f;
+    if (cgp < ng) {
+      int c = cgp;
+      for (; c + 7 * ng < C; c += 8 * ng) {
+        float wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = w2[(size_t)(c + u * ng) * R + jj];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part = fmaf(dz2[c + u * ng], wv[u], part);
       }
+      for (; c < C; c += ng) part = fmaf(dz2[c], w2[(size_t)c * R + jj], part);
+    }
+    __syncthreads();                       // A1/A2/dz2 are complete; reuse cs0 as the group scratch
+    float* scr = reinterpret_cast<float*>(cs0);
+    if (cgp < ng) scr[cgp * R + jj] = part;
+    __syncthreads();
+    if ((int)threadIdx.x < R) {
+      double acc = 0.0;
+      for (int q = 0; q < ng; ++q) acc += (double)scr[q * R + threadIdx.x];
+      const float t = hidden[(size_t)b * R + threadIdx.x] > 0.f ? (float)acc : 0.f;
+      dz1[threadIdx.x] = t;
+      dz1o[(size_t)b * R + threadIdx.x] = t;
     }
     __syncthreads();
   }
@@ -428,8 +518,17 @@ __global__ void __launch_bounds__(256)
     float g1, g2;
     if (has_se) {
       float dp = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < R; ++j) dp = fmaf(dz1[j], w1[(size_t)j * C + c], dp);
+      {
+        int j = 0;
+        for (; j + 8 <= R; j += 8) {            // eight independent (coalesced) loads per trip
+          float wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = w1[(size_t)(j + u) * C + c];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dp = fmaf(dz1[j + u], wv[u], dp);
+        }
+        for (; j < R; ++j) dp = fmaf(dz1[j], w1[(size_t)j * C + c], dp);
+      }
       dp /= (float)P;
       dpoolo[(size_t)b * C + c] = dp;
       const float s = gate[(size_t)b * C + c];
@@ -650,6 +749,157 @@ __global__ void __launch_bounds__(kGnThreads)
   }
 }
 
+// ------------------------------------------------------------------ forward: normalise + relu + rescale + bilinear x2
+// Decoder blocks feed an nn.Upsample(x2, bilinear, align_corners=False) (reference: src/models/beta_vae.py:52-53): the
+// activation relu(gn(y)) * gate is never written at its own resolution -- every thread owns one INPUT vector (b, h, w, c),
+// activates its 3x3 neighbourhood on the fly (one FMA + max per element, coefficients of its (sample, channel) in
+// registers) and writes the four output pixels it is the centre of.  Stencil as in upsample.cu:
+//   out[2i] = .25 a[i-1] + .75 a[i],  out[2i+1] = .75 a[i] + .25 a[i+1]   (edge-clamped, rows then columns).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gn_apply_up_kernel(const T* __restrict__ y, T* __restrict__ up, const float* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ gate,
+                       int H, int W, int C, int cv, int vec_per_sample) {
+  constexpr int V = Vec16<T>::N;
+  const int b = blockIdx.y;
+  const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+  const T* yb = y + (size_t)b * H * W * C;
+  T* ub = up + (size_t)b * 4 * H * W * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_sample; i += gridDim.x * blockDim.x) {
+    const int c = i % cv;
+    const int pix = i / cv;
+    const int w = pix % W, h = pix / W;
+    float zs[V], bs_[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float sc = gate ? gate[(size_t)b * C + c * V + k] : 1.f;
+      zs[k] = rstd * gamma[c * V + k] * sc;
+      bs_[k] = beta[c * V + k] * sc;
+    }
+    const int hs[3] = {max(h - 1, 0), h, min(h + 1, H - 1)}, ws[3] = {max(w - 1, 0), w, min(w + 1, W - 1)};
+    Vec16<T> n[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) n[a][d].load(yb + ((size_t)hs[a] * W + ws[d]) * C + (size_t)c * V);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          // round to the storage type first: bit-identical to materialising the activation and upsampling it
+          const float act = fmaxf(fmaf(n[a][d].v[k] - mean, zs[k], bs_[k]), 0.f);
+          n[a][d].v[k] = Elem<T>::to_f(Elem<T>::from_f(act));
+        }
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh) {
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const int ra = dh == 0 ? 0 : 1, rb = dh == 0 ? 1 : 2;
+        const float wa = dh == 0 ? 0.25f : 0.75f, wb = dh == 0 ? 0.75f : 0.25f;
+        const int ca = dw == 0 ? 0 : 1, cb = dw == 0 ? 1 : 2;
+        const float va = dw == 0 ? 0.25f : 0.75f, vb = dw == 0 ? 0.75f : 0.25f;
+        Vec16<T> o;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float top = va * n[ra][ca].v[k] + vb * n[ra][cb].v[k];
+          const float bot = va * n[rb][ca].v[k] + vb * n[rb][cb].v[k];
+          o.v[k] = wa * top + wb * bot;
+        }
+        o.store(ub + ((size_t)(2 * h + dh) * (2 * W) + (2 * w + dw)) * C + (size_t)c * V);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward: bilinear x2 backward + per-(sample,channel) sums
+// d_up [B][2H][2W][C] is the gradient w.r.t. the upsampled activation.  dout = upsample2x_bwd(d_up) (the transposed
+// stencil of upsample.cu, gathered) is written once as a workspace tensor and, in the same pass, enters the
+// A1 = sum dout*m and A2 = sum dout*m*xhat partial sums of gn_bwd_reduce_kernel (same chunk geometry, same order).
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads)
+    gn_bwd_reduce_up_kernel(const T* __restrict__ dup, const T* __restrict__ y, T* __restrict__ dout,
+                            const float* __restrict__ stats, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float* __restrict__ a1part, float* __restrict__ a2part,
+                            int H, int W, int C, int cv, int rows, int pc) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];
+  const int P = H * W, H2 = 2 * H, W2 = 2 * W;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  const int p0 = chunk * pc, p1 = min(P, p0 + pc);
+  float za[V], bt[V], a1[V], a2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    za[i] = rstd * gamma[col * V + i];
+    bt[i] = beta[col * V + i];
+    a1[i] = 0.f;
+    a2[i] = 0.f;
+  }
+  const size_t off = ((size_t)b * P) * C + (size_t)col * V;
+  const T* db = dup + (size_t)b * H2 * W2 * C + (size_t)col * V;
+  const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  for (int p = p0 + row; row < rows && p < p1; p += rows) {
+    const int h = p / W, w = p % W;
+    const int hs[4] = {max(2 * h - 1, 0), 2 * h, 2 * h + 1, min(2 * h + 2, H2 - 1)};
+    const int ws[4] = {max(2 * w - 1, 0), 2 * w, 2 * w + 1, min(2 * w + 2, W2 - 1)};
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float rowacc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) rowacc[k] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        Vec16<T> g;
+        g.load(db + ((size_t)hs[a] * W2 + ws[d]) * C);
+#pragma unroll
+        for (int k = 0; k < V; ++k) rowacc[k] = fmaf(wt[d], g.v[k], rowacc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = fmaf(wt[a], rowacc[k], acc[k]);
+    }
+    Vec16<T> v, d;
+    v.load(y + off + (size_t)p * C);
+#pragma unroll
+    for (int k = 0; k < V; ++k) d.v[k] = Elem<T>::to_f(Elem<T>::from_f(acc[k]));   // what the apply pass will read back
+    d.store(dout + off + (size_t)p * C);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float vm = v.v[i] - mean;
+      const float dm = (fmaf(vm, za[i], bt[i]) > 0.f) ? d.v[i] : 0.f;
+      a1[i] += dm;
+      a2[i] = fmaf(dm, vm, a2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) a2[i] *= rstd;
+  float* s0 = sm;
+  float* s1 = sm + rows * C;
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      s0[row * C + col * V + i] = a1[i];
+      s1[row * C + col * V + i] = a2[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a = 0.0, q = 0.0;  // fixed-order, double: these sums cancel heavily downstream
+    for (int r = 0; r < rows; ++r) {
+      a += (double)s0[r * C + c];
+      q += (double)s1[r * C + c];
+    }
+    const size_t o = ((size_t)b * nchunks + chunk) * C + c;
+    a1part[o] = (float)a;
+    a2part[o] = (float)q;
+  }
+}
+
 static int launch_gn_params(const float* G1, const float* G2, const float* dz2, const float* dz1, const float* cpos,
                             const float* spos, const float* hidden, const float* gamma, const float* beta,
                             float* dgamma, float* dbeta, float* dw1, float* db1, float* dw2, float* db2, int B, int P,
@@ -680,11 +930,12 @@ struct GnWs {
   float* dpool;   // [B][C]
   float* dz1;     // [B][Rmax=C]
   float* coef;    // [B][2]
+  void* dout;     // [B][P][C] elements (fused-upsample backward only)
   size_t bytes;
 };
 
-static GnWs gn_ws_carve(void* base, int B, int P, int C) {
-  const int nch = gn_num_chunks(P, C);
+static GnWs gn_ws_carve(void* base, int B, int P, int C, size_t dout_bytes = 0) {
+  const int nch = gn_max_chunks(B, P, C);
   GnWs w;
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
@@ -702,54 +953,90 @@ static GnWs gn_ws_carve(void* base, int B, int P, int C) {
   w.dpool = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
   w.dz1 = reinterpret_cast<float*>(take((size_t)B * C * sizeof(float)));
   w.coef = reinterpret_cast<float*>(take((size_t)B * 2 * sizeof(float)));
+  w.dout = dout_bytes ? take(dout_bytes) : nullptr;
   w.bytes = off;
   return w;
 }
 
+// Which kernels serve a shape.  Measured on B200 (profiles/r2_gn_paths.txt): every dependent phase of these latency-bound
+// ops costs ~1 us, so for samples that fit a cluster's shared memory (<= 1 MB) the ONE-launch cluster-resident kernels
+// (gn_se_cluster.cu, ~8 phases) beat the streaming passes (4 launches x ~3 phases) even with the bilinear x2 fused into
+// the latter: 13-17 us vs 22-32 us forward at batch 32.  Larger samples (dec3 of the default config: 2 MB) stream.
+// BVAE_GN_CLUSTER=0 / 1 forces the streaming / cluster kernels (the tests run both).
+static int gn_cluster_pref() {
+  const char* e = getenv("BVAE_GN_CLUSTER");
+  return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+}
+static bool gn_want_cluster(bool /*exact_fp32*/) { return gn_cluster_pref() != 0; }
+
+// up != 0: `out` is the bilinear x2 upsample of the activation, [B][2H][2W][C].
+// stat_part: optional [B][n_stat_part][2] doubles (sum, sum of squares) produced by the convolution's epilogue.
 template <typename T>
 static int gn_fwd_impl(const T* y, T* out, const float* gamma, const float* beta, const float* w1, const float* b1,
-                       const float* w2, const float* b2, int B, int P, int C, int R, float* stats, float* cpos,
-                       float* spos, float* hidden, float* gate, void* ws, cudaStream_t st) {
+                       const float* w2, const float* b2, int B, int H, int W, int C, int R, int up, float* stats,
+                       float* cpos, float* spos, float* hidden, float* gate, const double* stat_part, int n_stat_part,
+                       void* ws, cudaStream_t st) {
+  const int P = H * W;
   GnGeom g;
-  BVAE_REQUIRE(gn_geom(P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
+  BVAE_REQUIRE(gn_geom(B, P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
                "gn_relu_se: C=%d must be a multiple of %d with C/%d <= 256", C, Vec16<T>::N, Vec16<T>::N);
   GnWs w = gn_ws_carve(ws, B, P, C);
-  {
+  if (!up && !stat_part && gn_want_cluster(sizeof(T) == 4)) {
     bool handled = false;   // one cluster-resident kernel when the sample fits a cluster's shared memory
     const int rc = gn_cluster_fwd<T>(y, out, gamma, beta, w1, b1, w2, b2, B, P, C, R, stats, cpos, spos, hidden, gate, st,
                                      &handled);
     if (rc != BVAE_OK || handled) return rc;
   }
   dim3 grid(g.nchunks, B);
-  gn_stats_kernel<T><<<grid, g.threads, 0, st>>>(y, w.spart, P, C, g.cv, g.rows, g.pc);
-  BVAE_LAUNCH_CHECK("gn_stats");
+  const double* sp = stat_part;
+  int nsp = n_stat_part;
+  if (!sp) {
+    gn_stats_kernel<T><<<grid, g.threads, 0, st>>>(y, w.spart, P, C, g.cv, g.rows, g.pc);
+    BVAE_LAUNCH_CHECK("gn_stats");
+    sp = w.spart;
+    nsp = g.nchunks;
+  }
   const bool has_se = w1 != nullptr;
   if (has_se) {
     const size_t sm = (size_t)2 * g.rows * C * sizeof(float);
-    gn_pool_kernel<T><<<grid, g.threads, sm, st>>>(y, w.spart, gamma, beta, w.p0, w.p1, stats, P, C, g.cv, g.rows,
-                                                   g.pc);
+    gn_pool_kernel<T><<<grid, g.threads, sm, st>>>(y, sp, nsp, gamma, beta, w.p0, w.p1, stats, P, C, g.cv, g.rows, g.pc);
     BVAE_LAUNCH_CHECK("gn_pool");
-    se_excite_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(w.p0, w.p1, g.nchunks, gamma, beta, w1, b1, w2,
+    se_excite_kernel<<<B, kExThreads, (size_t)(C + R + 4) * sizeof(float), st>>>(w.p0, w.p1, g.nchunks, gamma, beta, w1, b1, w2,
                                                                       b2, cpos, spos, hidden, gate, P, C, R);
     BVAE_LAUNCH_CHECK("se_excite");
+  } else {
+    gn_finalize_stats_kernel<<<cdiv(B, 8), 256, 0, st>>>(sp, nsp, (double)P * C, stats, B);
+    BVAE_LAUNCH_CHECK("gn_finalize_stats");
   }
-  gn_scale_kernel<T><<<grid, g.threads, 0, st>>>(y, out, w.spart, gamma, beta, has_se ? gate : nullptr, stats, P, C,
-                                                 g.cv, g.rows, g.pc);
-  BVAE_LAUNCH_CHECK("gn_scale");
+  if (up) {
+    const int vps = P * g.cv;
+    int bx = cdiv(vps, 256);
+    const int cap = cdiv(16 * num_sms(), B);
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    gn_apply_up_kernel<T><<<dim3(bx, B), 256, 0, st>>>(y, out, stats, gamma, beta, has_se ? gate : nullptr, H, W, C, g.cv,
+                                                        vps);
+    BVAE_LAUNCH_CHECK("gn_apply_up");
+  } else {
+    gn_scale_kernel<T><<<grid, g.threads, 0, st>>>(y, out, stats, gamma, beta, has_se ? gate : nullptr, P, C, g.cv, g.rows,
+                                                   g.pc);
+    BVAE_LAUNCH_CHECK("gn_scale");
+  }
   return BVAE_OK;
 }
 
+// up != 0: `dout` is the gradient w.r.t. the UPSAMPLED activation, [B][2H][2W][C]; ws then also holds dout at [B][H][W][C].
 template <typename T>
 static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, const float* beta, const float* w1,
-                       const float* w2, int B, int P, int C, int R, const float* stats, const float* cpos,
+                       const float* w2, int B, int H, int W, int C, int R, int up, const float* stats, const float* cpos,
                        const float* spos, const float* hidden, const float* gate, float* dgamma, float* dbeta,
                        float* dw1, float* db1, float* dw2, float* db2, void* ws, cudaStream_t st) {
+  const int P = H * W;
   GnGeom g;
-  BVAE_REQUIRE(gn_geom(P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
+  BVAE_REQUIRE(gn_geom(B, P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
                "gn_relu_se: C=%d must be a multiple of %d with C/%d <= 256", C, Vec16<T>::N, Vec16<T>::N);
-  GnWs w = gn_ws_carve(ws, B, P, C);
+  GnWs w = gn_ws_carve(ws, B, P, C, up ? (size_t)B * P * C * sizeof(T) : 0);
   const bool has_se = w1 != nullptr;
-  {
+  if (!up && gn_want_cluster(sizeof(T) == 4)) {
     bool handled = false;
     const int rc = gn_cluster_bwd<T>(dout, y, dy, gamma, beta, w1, w2, B, P, C, R, stats, cpos, spos, hidden, gate, w.G1,
                                      w.G2, w.dz2, w.dz1, st, &handled);
@@ -760,22 +1047,28 @@ static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, con
   }
   dim3 grid(g.nchunks, B);
   const size_t sm = (size_t)2 * g.rows * C * sizeof(float);
-  gn_bwd_reduce_kernel<T><<<grid, g.threads, sm, st>>>(dout, y, stats, gamma, beta, w.p0, w.p1, P, C, g.cv, g.rows,
-                                                       g.pc);
-  BVAE_LAUNCH_CHECK("gn_bwd_reduce");
-  gn_bwd_mid_kernel<<<B, 256, (size_t)(3 * C + (has_se ? R : 0)) * sizeof(float), st>>>(
+  const T* d_lo = dout;
+  if (up) {
+    T* dlo = reinterpret_cast<T*>(w.dout);
+    gn_bwd_reduce_up_kernel<T><<<grid, g.threads, sm, st>>>(dout, y, dlo, stats, gamma, beta, w.p0, w.p1, H, W, C, g.cv,
+                                                            g.rows, g.pc);
+    BVAE_LAUNCH_CHECK("gn_bwd_reduce_up");
+    d_lo = dlo;
+  } else {
+    gn_bwd_reduce_kernel<T><<<grid, g.threads, sm, st>>>(dout, y, stats, gamma, beta, w.p0, w.p1, P, C, g.cv, g.rows,
+                                                         g.pc);
+    BVAE_LAUNCH_CHECK("gn_bwd_reduce");
+  }
+  gn_bwd_mid_kernel<<<B, kExThreads, (size_t)(3 * C + (has_se ? R : 0)) * sizeof(float), st>>>(
       w.p0, w.p1, g.nchunks, gamma, beta, w1, w2, cpos, spos, hidden, gate, w.G1, w.G2, w.dz2, w.dz1, w.dpool, w.coef,
       P, C, R);
   BVAE_LAUNCH_CHECK("gn_bwd_mid");
-  {
-    const int rc = launch_gn_params(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2,
-                                    db2, B, P, C, R, has_se, st);
-    if (rc != BVAE_OK) return rc;
-  }
-  gn_bwd_apply_kernel<T><<<grid, g.threads, 0, st>>>(dout, y, dy, stats, gamma, beta, has_se ? gate : nullptr,
+  gn_bwd_apply_kernel<T><<<grid, g.threads, 0, st>>>(d_lo, y, dy, stats, gamma, beta, has_se ? gate : nullptr,
                                                      w.dpool, w.coef, P, C, g.cv, g.rows, g.pc);
   BVAE_LAUNCH_CHECK("gn_bwd_apply");
-  return BVAE_OK;
+  // parameter gradients last: they are off the critical path of the data gradient
+  return launch_gn_params(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2, B,
+                          P, C, R, has_se, st);
 }
 
 }  // namespace bvae
@@ -787,27 +1080,77 @@ extern "C" size_t bvae_gn_relu_se_workspace(int B, int P, int C) {
   return gn_ws_carve(nullptr, B, P, C).bytes;
 }
 
-extern "C" int bvae_gn_relu_se_fwd(const void* y, void* out, const float* gamma, const float* beta, const float* w1,
-                                   const float* b1, const float* w2, const float* b2, int B, int P, int C, int R,
-                                   float* stats, float* cpos, float* spos, float* hidden, float* gate, void* ws,
-                                   size_t ws_bytes, int dtype, bvae_stream_t stream) {
+extern "C" size_t bvae_gn_relu_se_up_workspace(int B, int H, int W, int C) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
+  return gn_ws_carve(nullptr, B, H * W, C, (size_t)B * H * W * C * sizeof(float)).bytes;
+}
+
+static int gn_fwd_entry(const void* y, void* out, const float* gamma, const float* beta, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int B, int H, int W, int C, int R, int up, float* stats,
+                        float* cpos, float* spos, float* hidden, float* gate, const double* stat_part, int n_stat_part,
+                        void* ws, size_t ws_bytes, int dtype, bvae_stream_t stream) {
   BVAE_REQUIRE(y && out && gamma && beta && stats && ws, BVAE_ERR_ARG, "gn_relu_se_fwd: null pointer");
-  BVAE_REQUIRE(B > 0 && P > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_fwd: empty shape B=%d P=%d C=%d", B, P, C);
+  BVAE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_fwd: empty shape B=%d P=%d C=%d", B, H * W, C);
+  BVAE_REQUIRE(stat_part == nullptr || n_stat_part > 0, BVAE_ERR_ARG, "gn_relu_se_fwd: stat_part without a count");
   if (w1) {
     BVAE_REQUIRE(b1 && w2 && b2 && cpos && spos && hidden && gate && R > 0, BVAE_ERR_ARG,
                  "gn_relu_se_fwd: SE requested but SE buffers missing");
     BVAE_REQUIRE((size_t)(C + R) * 4 <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "gn_relu_se: C+R too large");
   }
-  BVAE_REQUIRE(ws_bytes >= bvae_gn_relu_se_workspace(B, P, C), BVAE_ERR_WORKSPACE, "gn_relu_se_fwd: workspace %zu < %zu",
-               ws_bytes, bvae_gn_relu_se_workspace(B, P, C));
+  const size_t need = up ? bvae_gn_relu_se_up_workspace(B, H, W, C) : bvae_gn_relu_se_workspace(B, H * W, C);
+  BVAE_REQUIRE(ws_bytes >= need, BVAE_ERR_WORKSPACE, "gn_relu_se_fwd: workspace %zu < %zu", ws_bytes, need);
   cudaStream_t st = as_stream(stream);
   if (dtype == BVAE_F32)
-    return gn_fwd_impl<float>((const float*)y, (float*)out, gamma, beta, w1, b1, w2, b2, B, P, C, R, stats, cpos,
-                              spos, hidden, gate, ws, st);
+    return gn_fwd_impl<float>((const float*)y, (float*)out, gamma, beta, w1, b1, w2, b2, B, H, W, C, R, up, stats, cpos,
+                              spos, hidden, gate, stat_part, n_stat_part, ws, st);
   if (dtype == BVAE_BF16)
-    return gn_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)y, (__nv_bfloat16*)out, gamma, beta, w1, b1, w2, b2, B, P,
-                                      C, R, stats, cpos, spos, hidden, gate, ws, st);
+    return gn_fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)y, (__nv_bfloat16*)out, gamma, beta, w1, b1, w2, b2, B, H, W,
+                                      C, R, up, stats, cpos, spos, hidden, gate, stat_part, n_stat_part, ws, st);
   BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "gn_relu_se_fwd: dtype %d", dtype);
+}
+
+static int gn_bwd_entry(const void* dout, const void* y, void* dy, const float* gamma, const float* beta, const float* w1,
+                        const float* w2, int B, int H, int W, int C, int R, int up, const float* stats, const float* cpos,
+                        const float* spos, const float* hidden, const float* gate, float* dgamma, float* dbeta,
+                        float* dw1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
+                        bvae_stream_t stream) {
+  BVAE_REQUIRE(dout && y && dy && gamma && beta && stats && dgamma && dbeta && ws, BVAE_ERR_ARG,
+               "gn_relu_se_bwd: null pointer");
+  BVAE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_bwd: empty shape");
+  if (w1) {
+    BVAE_REQUIRE(w2 && cpos && spos && hidden && gate && dw1 && db1 && dw2 && db2 && R > 0, BVAE_ERR_ARG,
+                 "gn_relu_se_bwd: SE requested but SE buffers missing");
+    BVAE_REQUIRE((size_t)(3 * C + R) * 4 <= 48 * 1024 && R <= kExThreads, BVAE_ERR_UNSUPPORTED, "gn_relu_se: C / R too large");
+  }
+  const size_t need = up ? bvae_gn_relu_se_up_workspace(B, H, W, C) : bvae_gn_relu_se_workspace(B, H * W, C);
+  BVAE_REQUIRE(ws_bytes >= need, BVAE_ERR_WORKSPACE, "gn_relu_se_bwd: workspace small");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == BVAE_F32)
+    return gn_bwd_impl<float>((const float*)dout, (const float*)y, (float*)dy, gamma, beta, w1, w2, B, H, W, C, R, up,
+                              stats, cpos, spos, hidden, gate, dgamma, dbeta, dw1, db1, dw2, db2, ws, st);
+  if (dtype == BVAE_BF16)
+    return gn_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, gamma,
+                                      beta, w1, w2, B, H, W, C, R, up, stats, cpos, spos, hidden, gate, dgamma, dbeta,
+                                      dw1, db1, dw2, db2, ws, st);
+  BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "gn_relu_se_bwd: dtype %d", dtype);
+}
+
+extern "C" int bvae_gn_relu_se_fwd(const void* y, void* out, const float* gamma, const float* beta, const float* w1,
+                                   const float* b1, const float* w2, const float* b2, int B, int P, int C, int R,
+                                   float* stats, float* cpos, float* spos, float* hidden, float* gate,
+                                   const double* stat_part, int n_stat_part, void* ws, size_t ws_bytes, int dtype,
+                                   bvae_stream_t stream) {
+  return gn_fwd_entry(y, out, gamma, beta, w1, b1, w2, b2, B, P, 1, C, R, 0, stats, cpos, spos, hidden, gate, stat_part,
+                      n_stat_part, ws, ws_bytes, dtype, stream);
+}
+
+extern "C" int bvae_gn_relu_se_up_fwd(const void* y, void* out_up, const float* gamma, const float* beta, const float* w1,
+                                      const float* b1, const float* w2, const float* b2, int B, int H, int W, int C,
+                                      int R, float* stats, float* cpos, float* spos, float* hidden, float* gate,
+                                      const double* stat_part, int n_stat_part, void* ws, size_t ws_bytes, int dtype,
+                                      bvae_stream_t stream) {
+  return gn_fwd_entry(y, out_up, gamma, beta, w1, b1, w2, b2, B, H, W, C, R, 1, stats, cpos, spos, hidden, gate, stat_part,
+                      n_stat_part, ws, ws_bytes, dtype, stream);
 }
 
 extern "C" int bvae_gn_relu_se_bwd(const void* dout, const void* y, void* dy, const float* gamma, const float* beta,
@@ -818,22 +1161,25 @@ extern "C" int bvae_gn_relu_se_bwd(const void* dout, const void* y, void* dy, co
                                    bvae_stream_t stream) {
   (void)b1;
   (void)b2;
-  BVAE_REQUIRE(dout && y && dy && gamma && beta && stats && dgamma && dbeta && ws, BVAE_ERR_ARG,
-               "gn_relu_se_bwd: null pointer");
-  BVAE_REQUIRE(B > 0 && P > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_bwd: empty shape");
-  if (w1) {
-    BVAE_REQUIRE(w2 && cpos && spos && hidden && gate && dw1 && db1 && dw2 && db2 && R > 0, BVAE_ERR_ARG,
-                 "gn_relu_se_bwd: SE requested but SE buffers missing");
-    BVAE_REQUIRE((size_t)(3 * C + R) * 4 <= 48 * 1024, BVAE_ERR_UNSUPPORTED, "gn_relu_se: C too large");
-  }
-  BVAE_REQUIRE(ws_bytes >= bvae_gn_relu_se_workspace(B, P, C), BVAE_ERR_WORKSPACE, "gn_relu_se_bwd: workspace small");
-  cudaStream_t st = as_stream(stream);
-  if (dtype == BVAE_F32)
-    return gn_bwd_impl<float>((const float*)dout, (const float*)y, (float*)dy, gamma, beta, w1, w2, B, P, C, R, stats,
-                              cpos, spos, hidden, gate, dgamma, dbeta, dw1, db1, dw2, db2, ws, st);
-  if (dtype == BVAE_BF16)
-    return gn_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, gamma,
-                                      beta, w1, w2, B, P, C, R, stats, cpos, spos, hidden, gate, dgamma, dbeta, dw1,
-                                      db1, dw2, db2, ws, st);
-  BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "gn_relu_se_bwd: dtype %d", dtype);
+  return gn_bwd_entry(dout, y, dy, gamma, beta, w1, w2, B, P, 1, C, R, 0, stats, cpos, spos, hidden, gate, dgamma, dbeta,
+                      dw1, db1, dw2, db2, ws, ws_bytes, dtype, stream);
+}
+
+extern "C" int bvae_gn_relu_se_up_bwd(const void* d_up, const void* y, void* dy, const float* gamma, const float* beta,
+                                      const float* w1, const float* b1, const float* w2, const float* b2, int B, int H,
+                                      int W, int C, int R, const float* stats, const float* cpos, const float* spos,
+                                      const float* hidden, const float* gate, float* dgamma, float* dbeta, float* dw1,
+                                      float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
+                                      bvae_stream_t stream) {
+  (void)b1;
+  (void)b2;
+  return gn_bwd_entry(d_up, y, dy, gamma, beta, w1, w2, B, H, W, C, R, 1, stats, cpos, spos, hidden, gate, dgamma, dbeta,
+                      dw1, db1, dw2, db2, ws, ws_bytes, dtype, stream);
+}
+
+/* 1 when bvae_gn_relu_se_fwd would run the single-launch cluster-resident kernel for this shape (the caller then keeps
+ * the bilinear x2 as its own pass); 0 when the streaming passes run (the fused *_up_* entry points then save a pass). */
+extern "C" int bvae_gn_relu_se_prefers_unfused(int B, int P, int C, int R, int dtype) {
+  if (gn_cluster_pref() == 0) return 0;
+  return gn_cluster_eligible(B, P, C, R, dtype == BVAE_BF16 ? 2 : 4) ? 1 : 0;
 }

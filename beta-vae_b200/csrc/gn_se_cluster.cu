@@ -613,6 +613,12 @@ static int gc_launch(K kern, int CS, int B, size_t smem, cudaStream_t st, Args..
   return BVAE_OK;
 }
 
+bool gn_cluster_eligible(int B, int P, int C, int R, int elem_bytes) {
+  if (R > C) return false;
+  size_t smem = 0;
+  return gc_pick_cs(B, P, C, 16 / elem_bytes, (size_t)elem_bytes, 1, &smem) != 0;
+}
+
 template <typename T>
 int gn_cluster_fwd(const T* y, T* out, const float* gamma, const float* beta, const float* w1, const float* b1,
                    const float* w2, const float* b2, int B, int P, int C, int R, float* stats, float* cpos, float* spos,

@@ -72,11 +72,13 @@ class _FusedBlock(nn.Module):
     def _conv(self) -> nn.Conv2d:
         raise NotImplementedError
 
-    def forward(self, x, packs: ops.PackCache, key: str, dt: int):
+    def forward(self, x, packs: ops.PackCache, key: str, dt: int, up_after: bool = False):
+        """``x`` is the block's conv input (a decoder block's input arrives already upsampled); ``up_after`` makes the
+        block emit the bilinear x2 upsample of its activation, i.e. the NEXT decoder block's conv input."""
         conv = self._conv()
         w1, b1, w2, b2 = self.se.gate_params
         return ops.ConvGnSeBlock.apply(x, conv.weight, conv.bias, self.norm.weight, self.norm.bias, w1, b1, w2, b2,
-                                       packs, key, self.stride, self.upsample, dt)
+                                       packs, key, self.stride, bool(up_after), dt)
 
 
 class ConvBlock(_FusedBlock):
@@ -253,8 +255,12 @@ class BetaVAE(nn.Module):
         zc = float(self.latent_clamp) if self.latent_clamp is not None else 0.0
         self._prepack(dt, F32)
         h = ops.FcDec.apply(z, self.fc_dec.weight, self.fc_dec.bias, wd, bd, zc, dt, c, hs, ws)
-        for i, blk in enumerate(self.decoder_blocks):
-            h = blk(h, self._packs, f"decoder_blocks.{i}", dt)
+        blocks = list(self.decoder_blocks)
+        if blocks and blocks[0].upsample:
+            h = ops.Upsample2x.apply(h)                     # nn.Upsample in front of the first decoder conv
+        for i, blk in enumerate(blocks):
+            nxt = i + 1 < len(blocks) and blocks[i + 1].upsample
+            h = blk(h, self._packs, f"decoder_blocks.{i}", dt, up_after=nxt)
         return h
 
     def _draw_eps(self, n, device):

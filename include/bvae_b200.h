@@ -78,6 +78,12 @@ int bvae_pack_fcdec_weight(const float* w, const float* b, void* wd, float* bd, 
 int bvae_conv3x3_weight_layout(int H, int W, int Cin, int Cout, int stride, int dtype, int kind);
 int bvae_conv3x3_fprop(const void* x, const void* wp, const float* bias, void* y, int B, int H, int W,
                        int Cin, int Cout, int stride, int x_dtype, int y_dtype, bvae_stream_t stream);
+/* fprop that also emits, from its epilogue, per-sample partial (sum, sum of squares) of the stored y -- the
+ * GroupNorm(1,C) statistics of the block (beta_vae.py:43,63) without a pass over y:
+ *   stat_part [B][n][2] doubles, n = bvae_conv3x3_fprop_stats_parts(...) (0: not available for this shape). */
+int bvae_conv3x3_fprop_stats_parts(int H, int W, int Cin, int Cout, int stride, int x_dtype, int y_dtype);
+int bvae_conv3x3_fprop_stats(const void* x, const void* wp, const float* bias, void* y, double* stat_part, int B, int H,
+                             int W, int Cin, int Cout, int stride, int x_dtype, int y_dtype, bvae_stream_t stream);
 /* dx = conv_transpose(dy, w); wp_t is the layout-0, transpose=1 pack. */
 int bvae_conv3x3_dgrad(const void* dy, const void* wp_t, void* dx, int B, int H, int W, int Cin, int Cout,
                        int stride, int dtype, bvae_stream_t stream);
@@ -116,10 +122,13 @@ int bvae_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, in
  * spos [B][C] = sum of xhat over positive pixels; hidden [B][R]; gate [B][C].
  * ---------------------------------------------------------------------------------------- */
 size_t bvae_gn_relu_se_workspace(int B, int P, int C);
+/* stat_part (optional, may be NULL): [B][n_stat_part][2] doubles = per-sample partial (sum, sum of squares) of y that
+ * the convolution's epilogue produced (bvae_conv3x3_fprop_stats); without it a statistics pass over y runs first. */
 int bvae_gn_relu_se_fwd(const void* y, void* out, const float* gamma, const float* beta, const float* w1,
                         const float* b1, const float* w2, const float* b2, int B, int P, int C, int R,
-                        float* stats, float* cpos, float* spos, float* hidden, float* gate, void* ws,
-                        size_t ws_bytes, int dtype, bvae_stream_t stream);
+                        float* stats, float* cpos, float* spos, float* hidden, float* gate,
+                        const double* stat_part, int n_stat_part, void* ws, size_t ws_bytes, int dtype,
+                        bvae_stream_t stream);
 /* dy may alias dout.  Parameter gradients are fp32, reference layout, overwritten (not accumulated). */
 int bvae_gn_relu_se_bwd(const void* dout, const void* y, void* dy, const float* gamma, const float* beta,
                         const float* w1, const float* b1, const float* w2, const float* b2, int B, int P,
@@ -127,6 +136,26 @@ int bvae_gn_relu_se_bwd(const void* dout, const void* y, void* dy, const float* 
                         const float* hidden, const float* gate, float* dgamma, float* dbeta, float* dw1,
                         float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
                         bvae_stream_t stream);
+/* The same block followed by the NEXT decoder block's nn.Upsample(x2, bilinear, align_corners=False)
+ * (beta_vae.py:52-53), fused: the activation is never written at its own resolution.
+ *   fwd: y [B][H][W][C] -> out_up [B][2H][2W][C] = upsample2x(relu(gn(y)) * gate)
+ *   bwd: d_up [B][2H][2W][C] (gradient w.r.t. out_up) -> dy [B][H][W][C]; upsample2x_bwd(d_up) lives in the workspace.
+ * Bit-identical to bvae_gn_relu_se_* composed with bvae_upsample2x_*. */
+size_t bvae_gn_relu_se_up_workspace(int B, int H, int W, int C);
+/* 1: this shape is served by the single-launch cluster-resident kernel (keep the upsample as its own pass); 0: the
+ * streaming passes run, and the fused entry points below save one write + one read of the activation. */
+int bvae_gn_relu_se_prefers_unfused(int B, int P, int C, int R, int dtype);
+int bvae_gn_relu_se_up_fwd(const void* y, void* out_up, const float* gamma, const float* beta, const float* w1,
+                           const float* b1, const float* w2, const float* b2, int B, int H, int W, int C, int R,
+                           float* stats, float* cpos, float* spos, float* hidden, float* gate,
+                           const double* stat_part, int n_stat_part, void* ws, size_t ws_bytes, int dtype,
+                           bvae_stream_t stream);
+int bvae_gn_relu_se_up_bwd(const void* d_up, const void* y, void* dy, const float* gamma, const float* beta,
+                           const float* w1, const float* b1, const float* w2, const float* b2, int B, int H,
+                           int W, int C, int R, const float* stats, const float* cpos, const float* spos,
+                           const float* hidden, const float* gate, float* dgamma, float* dbeta, float* dw1,
+                           float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
+                           bvae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * mu/logvar heads + clamp + reparameterisation + KL + KL-side objective, fused

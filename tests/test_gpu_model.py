@@ -123,6 +123,30 @@ def test_fullsize_matches_reference_scalars_and_oracle(case, prec):
           f"tensors above rtol: {sum(r[1] > rtol for r in rows)}/{len(rows)}")
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_streaming_groupnorm_path_matches_cluster_path(prec, monkeypatch):
+    """BVAE_GN_CLUSTER=0 routes every block through the streaming GroupNorm passes -- statistics from the convolution's
+    epilogue, bilinear x2 fused into the normalise pass and its transposed stencil into the backward's reduction pass
+    (what the 2 MB samples of dec3 always use).  Loss and gradients must agree with the default kernel choice."""
+    import cfgs
+    cfg = cfgs.small(model__base_channels=64, model__num_blocks=2, data__image_size=64, model__latent_dim=16,
+                     loss__use_ffl=True, loss__ffl_weight=0.5)
+    torch.manual_seed(11)
+    m = build_model(cfg, None, prec)
+    m.cpu().apply(cfgs.weight_init).cuda()
+    g = torch.Generator().manual_seed(5)
+    x, eps = torch.rand(4, 1, 64, 64, generator=g), torch.randn(4, 16, generator=g)
+    kw = dict(beta=1.0, capacity=5.0, free_bits=0.0, capacity_weight=1.0)
+    monkeypatch.delenv("BVAE_GN_CLUSTER", raising=False)
+    out_a, g_a = run_loss(m, x, eps, kw)
+    monkeypatch.setenv("BVAE_GN_CLUSTER", "0")
+    out_b, g_b = run_loss(m, x, eps, kw)
+    tol = 2e-5 if prec == "fp32" else 1e-2
+    assert abs(float(out_a["total"]) - float(out_b["total"])) <= tol * abs(float(out_a["total"]))
+    whole = rel_err(torch.cat([g_b[k].flatten() for k in g_a]), torch.cat([g_a[k].flatten() for k in g_a]))
+    assert whole <= tol * (50 if prec == "fp32" else 1), whole       # fp32: ill-conditioned tensors, summation order
+
+
 def test_encode_decode_forward_api():
     import cfgs
     cfg = cfgs.small()

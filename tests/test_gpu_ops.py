@@ -108,6 +108,46 @@ def test_conv3x3_fprop_dgrad_wgrad(shape, prec):
         _conv_case(shape, prec.split("-")[0])
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (3, 32, 16, 128, 64), (2, 16, 32, 64, 128), (1, 32, 32, 256, 256),
+                                   (33, 16, 8, 64, 64)])
+def test_conv3x3_fprop_stats_epilogue(shape):
+    """bvae_conv3x3_fprop_stats: the same y as the plain fprop, plus per-sample (sum, sum of squares) partials of the
+    STORED (bf16) y that add up to the GroupNorm(1,C) statistics -- and GroupNorm fed with them equals GroupNorm that
+    computes its own."""
+    ops = _ops()
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(H + Cin + Cout)
+    x = nhwc(rnd(torch.randn(B, Cin, H, W, generator=g), torch.bfloat16), torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(dev())
+    b = torch.randn(Cout, generator=g).to(dev())
+    wp = ops.pack_conv(w, ops.BF16, False, ops.conv_weight_layout(H, W, Cin, Cout, 1, ops.BF16, 0))
+    y0 = ops.conv3x3_fprop(x, wp, b, Cout, 1, ops.BF16)
+    y, part = ops.conv3x3_fprop(x, wp, b, Cout, 1, ops.BF16, want_stats=True)
+    assert part is not None and part.dtype == torch.float64 and part.shape[0] == B and part.shape[2] == 2
+    assert torch.equal(y, y0)
+    yd = y.double()
+    tot = part.sum(dim=1)
+    assert torch.allclose(tot[:, 0], yd.sum(dim=(1, 2, 3)), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(tot[:, 1], yd.pow(2).sum(dim=(1, 2, 3)), rtol=1e-6, atol=1e-3)
+    gamma, beta = torch.ones(Cout, device=dev()), torch.zeros(Cout, device=dev())
+    import os
+    old = os.environ.get("BVAE_GN_CLUSTER")
+    os.environ["BVAE_GN_CLUSTER"] = "0"
+    try:
+        o1, s1 = ops.gn_relu_se_fwd(y, gamma, beta, None, None, None, None)
+        o2, s2 = ops.gn_relu_se_fwd(y, gamma, beta, None, None, None, None, stat_part=part)
+    finally:
+        if old is None:
+            del os.environ["BVAE_GN_CLUSTER"]
+        else:
+            os.environ["BVAE_GN_CLUSTER"] = old
+    assert rel_err(s2[0], s1[0]) <= 1e-6 and rel_err(o2, o1) <= 1e-2 * 0.5
+    # shapes the stride-1 halo kernel does not serve report "no statistics epilogue"
+    from bvae_rt.lib import query
+    assert query("bvae_conv3x3_fprop_stats_parts", 16, 16, 64, 64, 2, ops.BF16, ops.BF16) == 0
+    assert query("bvae_conv3x3_fprop_stats_parts", 16, 16, 64, 64, 1, ops.F32, ops.F32) == 0
+
+
 def _conv_case(shape, prec):
     ops = _ops()
     dtype, tol = DT[prec]
@@ -192,6 +232,7 @@ def _gn_se_ref(y, gamma, beta, se):
     return a * s[:, :, None, None]
 
 
+@pytest.mark.parametrize("path", ["stream", "cluster"])
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 8, 8, 8, 2), (3, 4, 4, 64, 8), (1, 16, 16, 16, 1), (2, 33, 9, 24, 3),
                                    (2, 64, 64, 8, 0), (4, 8, 8, 512, 64), (2, 8, 8, 16, 0),
@@ -200,7 +241,9 @@ def _gn_se_ref(y, gamma, beta, se):
                                    (2, 128, 128, 16, 0), (40, 16, 16, 64, 8),
                                    # tiled SE weight-gradient kernel: channel tail (72 = 2 * 32 + 8), batch tail (37 = 32 + 5)
                                    (3, 4, 4, 72, 40), (37, 4, 4, 128, 32)])
-def test_gn_relu_se(shape, prec):
+def test_gn_relu_se(shape, prec, path, monkeypatch):
+    # "stream" = the default multi-pass kernels; "cluster" = the cluster-resident kernels (BVAE_GN_CLUSTER=1, read per call)
+    monkeypatch.setenv("BVAE_GN_CLUSTER", "1" if path == "cluster" else "0")
     ops = _ops()
     dtype, tol = DT[prec]
     B, H, W, Cc, R = shape
@@ -231,6 +274,53 @@ def test_gn_relu_se(shape, prec):
     if se:
         for got, want in zip((dw1, db1, dw2, db2), se):
             assert rel_err(got, want.grad) <= ptol * 5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8, 2), (3, 4, 4, 64, 8), (2, 5, 7, 24, 3), (2, 16, 16, 256, 32), (32, 8, 8, 512, 64),
+                                   (3, 32, 32, 128, 16), (2, 64, 64, 64, 8), (2, 16, 16, 16, 0), (1, 1, 1, 8, 2)])
+def test_gn_relu_se_fused_upsample(shape, prec, monkeypatch):
+    """bvae_gn_relu_se_up_{fwd,bwd} (the decoder's activation emitted already upsampled, the transposed stencil fused into
+    the backward's reduction pass) against torch -- and bit-identical to the un-fused composition of the same
+    (streaming) kernels."""
+    monkeypatch.setenv("BVAE_GN_CLUSTER", "0")
+    ops = _ops()
+    dtype, tol = DT[prec]
+    B, H, W, Cc, R = shape
+    g = torch.Generator().manual_seed(7 * H + Cc + R)
+    y = rnd(torch.randn(B, Cc, H, W, generator=g) * 1.5 + 0.3, dtype).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(Cc, generator=g)).requires_grad_(True)
+    beta = (0.2 * torch.randn(Cc, generator=g)).requires_grad_(True)
+    se = None
+    if R > 0:
+        se = [(torch.randn(R, Cc, generator=g) / Cc ** 0.5).requires_grad_(True),
+              (0.1 * torch.randn(R, generator=g)).requires_grad_(True),
+              (torch.randn(Cc, R, generator=g) / R ** 0.5).requires_grad_(True),
+              (0.1 * torch.randn(Cc, generator=g)).requires_grad_(True)]
+    ref = F.interpolate(_gn_se_ref(y, gamma, beta, se), scale_factor=2, mode="bilinear", align_corners=False)
+    dup = rnd(torch.randn(ref.shape, generator=g), dtype)
+    ref.backward(dup)
+    D = lambda t: None if t is None else t.detach().to(dev())
+    sed = [D(t) for t in se] if se else [None] * 4
+    yd = nhwc(y.detach(), dtype)
+    up, saved = ops.gn_relu_se_fwd(yd, D(gamma), D(beta), *sed, up=True)
+    assert tuple(up.shape) == (B, 2 * H, 2 * W, Cc)
+    # bf16: the activation is rounded to bf16 before the stencil (as the un-fused path stores it), torch keeps fp32
+    assert rel_err(nchw(up), ref) <= tol * (1 if prec == "fp32" else 2)
+    dupd = nhwc(dup, dtype)
+    dy, dg, db, dw1, db1, dw2, db2 = ops.gn_relu_se_bwd(dupd, yd, D(gamma), D(beta), *sed, saved, up=True)
+    ptol = 1e-5 if prec == "fp32" else 2e-3
+    assert rel_err(nchw(dy), y.grad) <= tol * (1 if prec == "fp32" else 2)
+    assert rel_err(dg, gamma.grad) <= ptol * 3
+    assert rel_err(db, beta.grad) <= ptol * 3
+    if se:
+        for got, want in zip((dw1, db1, dw2, db2), se):
+            assert rel_err(got, want.grad) <= ptol * 5
+    # the fused kernels are the composition, bit for bit
+    out, saved2 = ops.gn_relu_se_fwd(yd, D(gamma), D(beta), *sed)
+    assert torch.equal(ops.upsample2x_fwd(out), up)
+    dy2 = ops.gn_relu_se_bwd(ops.upsample2x_bwd(dupd), yd, D(gamma), D(beta), *sed, saved2)[0]
+    assert torch.equal(dy2, dy)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
