@@ -62,7 +62,18 @@ def backward_ready_buckets(model) -> List[List[str]]:
 
 class TrainEngine:
     def __init__(self, model, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 decoupled_wd: bool = False, clip: float = 0.0, process_group=None, reduce_dtype=torch.float32):
+                 decoupled_wd: bool = False, clip: float = 0.0, process_group=None, reduce_dtype=torch.float32,
+                 dp_mode: Optional[str] = None):
+        """``dp_mode``: how the gradient exchange is issued when world > 1 --
+        "single": ONE all-reduce of the whole flat gradient buffer after backward (default);
+        "buckets": the four backward-ready buckets, each launched from a post-accumulate hook under the rest of backward.
+        Measured on 8 x B200 (profiles/): the persistent convolution kernels own every SM, so NCCL's CTAs only run at
+        kernel boundaries -- the bucketed launches cost more in disturbed kernels and launch latency than the exposed
+        ~100 us of one 38 MB NVLS all-reduce.  BVAE_DP_MODE overrides."""
+        import os
+        self.dp_mode = os.environ.get("BVAE_DP_MODE", dp_mode or "single")
+        if self.dp_mode not in ("single", "buckets"):
+            raise ValueError(f"dp_mode '{self.dp_mode}' (single | buckets)")
         self.model = model
         self.lr, self.betas, self.eps = float(lr), tuple(betas), float(eps)
         self.weight_decay, self.decoupled_wd, self.clip = float(weight_decay), bool(decoupled_wd), float(clip)
@@ -130,7 +141,7 @@ class TrainEngine:
                 view.copy_(g)                                  # autograd cloned or accumulated elsewhere
                 p.grad = view
             self._pending[bi] -= 1
-            if self._pending[bi] == 0 and self.world > 1:
+            if self._pending[bi] == 0 and self.world > 1 and self.dp_mode == "buckets":
                 self._launch_reduce(bi)
         return hook
 
@@ -156,7 +167,18 @@ class TrainEngine:
         self._works = []
 
     def finish_reduce(self):
-        """Wait for the bucket all-reduces (stream-side) and restore fp32 gradients."""
+        """Wait for the bucket all-reduces (stream-side) and restore fp32 gradients; in "single" mode issue the one
+        all-reduce of the whole gradient buffer here (backward has been enqueued in full at this point)."""
+        if self.world > 1 and self.dp_mode == "single":
+            self._zero_unused()                                 # stale slots must not be summed into other ranks' gradients
+            buf = self.flat_g
+            if self.reduce_dtype == torch.float32:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+            else:
+                low = buf.to(self.reduce_dtype)
+                dist.all_reduce(low, op=dist.ReduceOp.SUM, group=self.pg)
+                buf.copy_(low)
+            return
         for w, low, buf in self._works:
             w.wait()
             if low is not None:
@@ -356,11 +378,8 @@ class GraphedTrainStep:
         self.engine.step(from_device_scalars=True)
         # hand back plain tensors: a live autograd graph would pin this iteration's AccumulateGrad
         # nodes (and their stream) and break the capture that follows the eager steps
-        res = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
-        # the scalars a training loop logs, packed so one 16-byte device->host copy reads them all
-        res["scalars"] = torch.stack([res["total"].float(), res["recon"].float(), res["kl_mean"].float(),
-                                      res["recon_ffl"].float().to(res["total"].device)])
-        return res
+        # (the scalars a training loop logs arrive packed in out["scalars"]: one 16-byte device->host copy reads them all)
+        return {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
     def _capture(self, kw):
         from .lib import query

@@ -507,7 +507,9 @@ class FinalConvSigmoidRecon(torch.autograd.Function):
         Co = w.shape[0]
         dev = h.device
         recon = torch.empty((B, Co, H, W), dtype=torch.float32, device=dev)
-        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        # the loss scalar is written by the kernel whenever a target is given (no fill launch on the training path)
+        loss = torch.empty((), dtype=torch.float32, device=dev) if target is not None else \
+            torch.zeros((), dtype=torch.float32, device=dev)
         if target is not None:
             target = target.contiguous().float()
         ws = _ws(query("bvae_finalconv_workspace", B, H, W, Cc, Co), dev)
@@ -575,3 +577,71 @@ class FocalFrequencyCore(torch.autograd.Function):
         with profiler.region("ffl_bwd", nbytes=2.0 * spec_ri.numel() * 4):
             call("bvae_ffl_bwd", _p(spec_ri), _p(scale), _p(U), _p(g_loss), _p(g), B, Cc, H, Wh, W, alpha, eps, _stream())
         return g, None, None, None
+
+
+class FocalFrequencyImage(torch.autograd.Function):
+    """weight * FocalFrequencyLoss(pred, target) (src/training/losses.py:16-35) with the 2-D FFT in shared memory: one
+    CTA per image transforms pred - target, the spectrum-side arithmetic follows, and the backward runs the adjoint
+    transform -- no cuFFT, no complex ATen glue.  pred / target: [B, C, H, W] fp32."""
+
+    @staticmethod
+    def forward(ctx, pred, target, alpha, eps, weight):
+        B, Cc, H, W = pred.shape
+        pred = pred.contiguous().float()
+        target = target.contiguous().float()
+        dev = pred.device
+        spec = torch.empty((B, Cc, H, W // 2 + 1, 2), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        scale = torch.empty(Cc, dtype=torch.float32, device=dev)
+        U = torch.empty(Cc, dtype=torch.float32, device=dev)
+        ws = _ws(query("bvae_ffl_image_workspace", B, Cc, H, W), dev)
+        with profiler.region("ffl_image_fwd", nbytes=2.0 * pred.numel() * 4 + spec.numel() * 4):
+            call("bvae_ffl_image_fwd", _p(pred), _p(target), B, Cc, H, W, float(alpha), float(eps), float(weight), _p(spec),
+                 _p(loss), _p(scale), _p(U), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(spec, scale, U)
+        ctx.cfg = (tuple(pred.shape), float(alpha), float(eps), float(weight))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        spec, scale, U = ctx.saved_tensors
+        shape, alpha, eps, weight = ctx.cfg
+        B, Cc, H, W = shape
+        d_pred = torch.empty(shape, dtype=torch.float32, device=spec.device)
+        g_loss = g_loss.contiguous().float()
+        ws = _ws(query("bvae_ffl_image_workspace", B, Cc, H, W), spec.device)
+        with profiler.region("ffl_image_bwd", nbytes=spec.numel() * 4 + d_pred.numel() * 4):
+            call("bvae_ffl_image_bwd", _p(spec), _p(scale), _p(U), _p(g_loss), weight, _p(d_pred), _p(ws), ws.numel(), B, Cc,
+                 H, W, alpha, eps, _stream())
+        return d_pred, None, None, None, None
+
+
+def ffl_image_supported(H, W):
+    return query("bvae_ffl_image_supported", int(H), int(W)) == 1
+
+
+class LossCombine(torch.autograd.Function):
+    """recon = base + lpips + ffl; total = recon + kl_side (src/models/beta_vae.py:216-217, 249-253) in one launch.
+    Returns (total, recon, packed) where packed = [total, recon, kl_mean, recon_ffl, recon_base, recon_lpips]
+    (non-differentiable; its first four entries are what a training loop logs)."""
+
+    @staticmethod
+    def forward(ctx, base, lp, ff, sc):
+        out = torch.empty(6, dtype=torch.float32, device=base.device)
+        call("bvae_loss_combine_fwd", _p(base), _p(lp), _p(ff), _p(sc), _p(out), _stream())
+        ctx.has = (lp is not None, ff is not None)
+        ctx.set_materialize_grads(False)
+        packed = out.detach()
+        ctx.mark_non_differentiable(packed)
+        return out[0], out[1], packed
+
+    @staticmethod
+    def backward(ctx, g_total, g_rec, _g_packed):
+        ref = g_total if g_total is not None else g_rec
+        if ref is None:
+            return None, None, None, None
+        g = torch.empty(5, dtype=torch.float32, device=ref.device)
+        call("bvae_loss_combine_bwd", _p(None if g_total is None else g_total.contiguous().float()),
+             _p(None if g_rec is None else g_rec.contiguous().float()), _p(g), _stream())
+        has_lp, has_ff = ctx.has
+        return g[0], (g[0] if has_lp else None), (g[0] if has_ff else None), g[1:5]

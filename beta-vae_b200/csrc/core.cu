@@ -474,3 +474,52 @@ extern "C" int bvae_adam_clip_step_dev(float* p, const float* g, float* m, float
   BVAE_LAUNCH_CHECK("adam_clip_step_dev");
   return BVAE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The scalar tail of BetaVAE.loss (reference: src/models/beta_vae.py:216-217, 249-253):
+//   recon = recon_base + recon_lpips + recon_ffl,   total = recon + kl_side   (kl_side = beta*KL | gamma*|KL - C|, + latent reg)
+// as ONE launch each way instead of ~6 ATen fills / adds / a stack (and their autograd).  out[0..5] =
+// (total, recon, kl_mean, recon_ffl, recon_base, recon_lpips): out[0..3] is the 4-scalar vector a training loop logs.
+// Backward: (d recon_base, d recon_lpips, d recon_ffl) = g_total + g_recon each, d kl_side = g_total.
+// ---------------------------------------------------------------------------------------------
+namespace bvae {
+__global__ void loss_combine_fwd_kernel(const float* __restrict__ base, const float* __restrict__ lp,
+                                        const float* __restrict__ ff, const float* __restrict__ sc, float* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    const float b = base[0], l = lp ? lp[0] : 0.f, f = ff ? ff[0] : 0.f;
+    const float rec = (b + l) + f;
+    out[0] = rec + sc[2];
+    out[1] = rec;
+    out[2] = sc[0];
+    out[3] = f;
+    out[4] = b;
+    out[5] = l;
+  }
+}
+__global__ void loss_combine_bwd_kernel(const float* __restrict__ g_total, const float* __restrict__ g_rec,
+                                        float* __restrict__ g) {
+  if (threadIdx.x == 0) {
+    const float gt = g_total ? g_total[0] : 0.f, gr = g_rec ? g_rec[0] : 0.f;
+    g[0] = gt + gr;          // d recon_base = d recon_lpips = d recon_ffl
+    g[1] = 0.f;              // d sc[0] (kl_mean is returned detached from this op)
+    g[2] = 0.f;
+    g[3] = gt;               // d sc[2]
+    g[4] = 0.f;
+  }
+}
+}  // namespace bvae
+
+extern "C" int bvae_loss_combine_fwd(const float* recon_base, const float* recon_lpips, const float* recon_ffl,
+                                     const float* kl_scalars, float* out6, bvae_stream_t stream) {
+  BVAE_REQUIRE(recon_base && kl_scalars && out6, BVAE_ERR_ARG, "loss_combine_fwd: null pointer");
+  bvae::loss_combine_fwd_kernel<<<1, 32, 0, as_stream(stream)>>>(recon_base, recon_lpips, recon_ffl, kl_scalars, out6);
+  BVAE_LAUNCH_CHECK("loss_combine_fwd");
+  return BVAE_OK;
+}
+
+extern "C" int bvae_loss_combine_bwd(const float* g_total, const float* g_recon, float* g5, bvae_stream_t stream) {
+  BVAE_REQUIRE(g5 && (g_total || g_recon), BVAE_ERR_ARG, "loss_combine_bwd: null pointer");
+  bvae::loss_combine_bwd_kernel<<<1, 32, 0, as_stream(stream)>>>(g_total, g_recon, g5);
+  BVAE_LAUNCH_CHECK("loss_combine_bwd");
+  return BVAE_OK;
+}

@@ -20,15 +20,16 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict
                                                              int H, int W, int cv) {
   constexpr int V = Vec16<T>::N;
   const int C = cv * V;
-  const long long total = (long long)B * H * W * cv;  // one thread per INPUT vector -> 4 outputs
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv);
-    long long r = i / cv;
-    const int w = (int)(r % W);
-    r /= W;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
+  // one thread per INPUT vector -> 4 outputs.  32-bit index math: the launcher guarantees B*H*W*cv < 2^31 (64-bit
+  // div / mod sequences cost more instructions than the stencil itself)
+  const unsigned total = (unsigned)B * H * W * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)cv);
+    unsigned r = i / (unsigned)cv;
+    const int w = (int)(r % (unsigned)W);
+    r /= (unsigned)W;
+    const int h = (int)(r % (unsigned)H);
+    const int b = (int)(r / (unsigned)H);
     const int hm = max(h - 1, 0), hp = min(h + 1, H - 1), wm = max(w - 1, 0), wp = min(w + 1, W - 1);
     const T* xb = x + (size_t)b * H * W * C + (size_t)c * V;
     Vec16<T> n[3][3];
@@ -67,15 +68,14 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
   constexpr int V = Vec16<T>::N;
   const int C = cv * V;
   const int H2 = 2 * H, W2 = 2 * W;
-  const long long total = (long long)B * H * W * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv);
-    long long r = i / cv;
-    const int w = (int)(r % W);
-    r /= W;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
+  const unsigned total = (unsigned)B * H * W * cv;     // 32-bit index math, see the forward kernel
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)cv);
+    unsigned r = i / (unsigned)cv;
+    const int w = (int)(r % (unsigned)W);
+    r /= (unsigned)W;
+    const int h = (int)(r % (unsigned)H);
+    const int b = (int)(r / (unsigned)H);
     const T* db = dy + (size_t)b * H2 * W2 * C + (size_t)c * V;
     const int hs[4] = {max(2 * h - 1, 0), 2 * h, 2 * h + 1, min(2 * h + 2, H2 - 1)};
     const int ws[4] = {max(2 * w - 1, 0), 2 * w, 2 * w + 1, min(2 * w + 2, W2 - 1)};
@@ -110,6 +110,7 @@ static int upsample_launch(bool fwd, const void* in, void* out, int B, int H, in
   constexpr int V = Vec16<T>::N;
   BVAE_REQUIRE(C % V == 0, BVAE_ERR_UNSUPPORTED, "upsample2x: C=%d must be a multiple of %d", C, V);
   const long long total = (long long)B * H * W * (C / V);
+  BVAE_REQUIRE(total < (1LL << 31), BVAE_ERR_UNSUPPORTED, "upsample2x: tensor too large for 32-bit indexing");
   long long blocks = (total + 255) / 256;
   const long long cap = 16LL * num_sms();
   if (blocks > cap) blocks = cap;

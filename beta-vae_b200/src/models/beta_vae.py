@@ -330,22 +330,25 @@ class BetaVAE(nn.Module):
         recon, base_recon = ops.FinalConvSigmoidRecon.apply(
             feat, self.final_conv.weight, self.final_conv.bias, x, LOSS[self.recon_loss_type])
 
-        lp = torch.zeros((), device=dev)
-        ff = torch.zeros((), device=dev)
+        lp = ff = None
         if self.use_lpips and self.lpips_weight > 0:
             if self.lpips_loss is None:
                 self.lpips_loss = LPIPSLoss(net=self.lpips_net_name).to(dev)
             lp = self.lpips_loss(recon, x) * self.lpips_weight
         if self.use_ffl and self.ffl_weight > 0:
-            ff = self.ffl_loss(recon, x) * self.ffl_weight
-        rec_loss = base_recon + lp + ff
-        total = rec_loss + sc[2]          # sc[2] = beta*kl_eff | gamma*|kl_mean - C|, plus latent_reg
+            ff = self.ffl_loss(recon, x, weight=self.ffl_weight)
+        # sc[2] = beta*kl_eff | gamma*|kl_mean - C|, plus latent_reg; the scalar tail is one launch
+        total, rec_loss, packed = ops.LossCombine.apply(base_recon, lp, ff, sc)
         return {
             "total": total,
             "recon": rec_loss,
             "recon_base": base_recon.detach(),
-            "recon_lpips": lp.detach(),
-            "recon_ffl": ff.detach(),
+            "recon_lpips": packed[5],
+            "recon_ffl": packed[3],
+            # extra keys (not in the reference's dict): the logged scalars as ONE device vector,
+            # packed = [total, recon, kl_mean, recon_ffl, recon_base, recon_lpips]; scalars = its first four
+            "packed": packed,
+            "scalars": packed[:4],
             "kl_mean": sc[0],
             "kl_per_dim": kl_per_dim.detach(),
             "beta": torch.tensor(b),

@@ -206,7 +206,7 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
                   capacity_weight=capacity_weight_cfg if capacity is not None else None)
         model.set_beta(beta)
         model.train()
-        running = torch.zeros(6, device=device)     # total, recon, recon_base, recon_lpips, recon_ffl, kl
+        running = torch.zeros(6, device=device)     # packed order: total, recon, kl, recon_ffl, recon_base, recon_lpips
         last = None
         n_batches = 0
         for i, x in enumerate(_staged_images(train_loader, step_fn)):
@@ -225,9 +225,7 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
                 # plain tensors from here on: a live autograd graph would keep this step's AccumulateGrad nodes (and
                 # their stream) alive and invalidate the next graph capture (GraphedTrainStep._body does the same)
                 losses = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in losses.items()}
-            running += torch.stack([losses["total"].detach(), losses["recon"].detach(), losses["recon_base"],
-                                    losses["recon_lpips"].to(device), losses["recon_ffl"].to(device),
-                                    losses["kl_mean"].detach()]).float()
+            running += losses["packed"]             # the model's six logged scalars as one device vector
             last = losses
             n_batches = i + 1
             total_steps += 1
@@ -235,8 +233,8 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
                 r = (running / n_batches).tolist()          # the one device->host read of this logging interval
                 log_metrics({
                     "epoch": epoch, "beta": float(beta), "capacity": float(capacity) if capacity is not None else 0.0,
-                    "train_total_loss": r[0], "train_recon_loss": r[1], "train_recon_base": r[2],
-                    "train_recon_lpips": r[3], "train_recon_ffl": r[4], "train_kl": r[5], "train_kl_mean": r[5],
+                    "train_total_loss": r[0], "train_recon_loss": r[1], "train_recon_base": r[4],
+                    "train_recon_lpips": r[5], "train_recon_ffl": r[3], "train_kl": r[2], "train_kl_mean": r[2],
                     "train_kl_effective_last": float(last["kl_effective"]),
                     "train_kl_per_dim_mean": float(last["kl_per_dim"].mean()), "loss_mode": last["mode"],
                     "mu_mean_batch": float(last["mu"].mean()), "z_std_batch": float(last["z"].std()),
@@ -257,8 +255,7 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
                 if isinstance(x, (list, tuple)):
                     x = torch.stack(x, 0)
                 l = model.loss(x.to(device, non_blocking=True), **kw)
-                vsum += torch.stack([l["total"], l["recon"], l["recon_base"], l["recon_lpips"].to(device),
-                                     l["recon_ffl"].to(device), l["kl_mean"]]).float()
+                vsum += l["packed"]
                 vlast = l
                 vb += 1
                 if debug_enabled and j + 1 >= debug_cfg.max_val_batches:
@@ -278,11 +275,11 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
         if rank == 0:
             log_metrics({
                 "epoch": epoch, "beta": float(beta), "capacity": float(capacity) if capacity is not None else 0.0,
-                "val_total_loss": v[0], "val_recon_loss": v[1], "val_recon_base": v[2], "val_recon_lpips": v[3],
-                "val_recon_ffl": v[4], "val_kl": v[5],
+                "val_total_loss": v[0], "val_recon_loss": v[1], "val_recon_base": v[4], "val_recon_lpips": v[5],
+                "val_recon_ffl": v[3], "val_kl": v[2],
                 "val_kl_per_dim_mean": float(vlast["kl_per_dim"].mean()) if vlast is not None else nan,
                 "loss_mode": vlast["mode"] if vlast is not None else None,
-                "train_kl_mean": train_means[5],
+                "train_kl_mean": train_means[2],
                 "train_kl_effective_last": float(last["kl_effective"]) if last is not None else nan,
                 # the sklearn linear probe of the reference (train.py:24-96) is analysis code, out of scope
                 "latent_probe_auc": nan, "best_dim_auc": nan, "best_dim_corr": nan, "best_dim_r2": nan,

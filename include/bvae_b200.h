@@ -244,6 +244,27 @@ int bvae_ffl_fwd(const float* spec, int B, int C, int H, int Wh, int W, float al
                  float* scale, float* U, void* ws, size_t ws_bytes, bvae_stream_t stream);
 int bvae_ffl_bwd(const float* spec, const float* scale, const float* U, const float* g_loss, float* g_spec, int B,
                  int C, int H, int Wh, int W, float alpha, float eps, bvae_stream_t stream);
+/* The whole term on images, 1-D line FFTs in shared memory, rows then columns (power-of-two sides <= 128):
+ *   loss = weight * FFL(pred, target);  pred / target / d_pred [B][C][H][W] fp32 (NCHW);
+ *   spec [B][C][H][W/2+1][2] fp32 is the saved one-sided spectrum of pred - target (ortho), scale / U [C] as above. */
+int bvae_ffl_image_supported(int H, int W);
+size_t bvae_ffl_image_workspace(int B, int C, int H, int W);
+int bvae_ffl_image_fwd(const float* pred, const float* target, int B, int C, int H, int W, float alpha, float eps,
+                       float weight, float* spec, float* loss, float* scale, float* U, void* ws, size_t ws_bytes,
+                       bvae_stream_t stream);
+int bvae_ffl_image_bwd(const float* spec, const float* scale, const float* U, const float* g_loss, float weight,
+                       float* d_pred, void* ws, size_t ws_bytes, int B, int C, int H, int W, float alpha, float eps,
+                       bvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scalar tail of BetaVAE.loss (beta_vae.py:216-217, 249-253) in one launch each way:
+ *   recon = recon_base + recon_lpips + recon_ffl;  total = recon + kl_scalars[2]
+ *   out6 = (total, recon, kl_mean, recon_ffl, recon_base, recon_lpips); recon_lpips / recon_ffl may be NULL (= 0).
+ *   bwd: g5 = (d recon_base [= d lpips = d ffl], d kl_scalars[0..3]) from g_total / g_recon (either may be NULL).
+ * ---------------------------------------------------------------------------------------- */
+int bvae_loss_combine_fwd(const float* recon_base, const float* recon_lpips, const float* recon_ffl,
+                          const float* kl_scalars, float* out6, bvae_stream_t stream);
+int bvae_loss_combine_bwd(const float* g_total, const float* g_recon, float* g5, bvae_stream_t stream);
 
 /* Input pipeline: uint8 image bytes -> fp32 in [0, 1], dst[i] = float(src[i]) / 255 with IEEE division -- the values
  * torchvision's ToTensor produces from the dataset's PNGs (datautils.py:59-65), so shipping bytes over PCIe and

@@ -505,10 +505,13 @@ def test_errors_are_loud():
 
 
 @pytest.mark.parametrize("alpha", [1.0, 0.5, 2.0])
-@pytest.mark.parametrize("shape", [(4, 1, 32, 32), (2, 3, 16, 24), (3, 1, 8, 9), (32, 1, 128, 128)])
+@pytest.mark.parametrize("shape", [(4, 1, 32, 32), (2, 3, 16, 24), (3, 1, 8, 9), (32, 1, 128, 128),
+                                   # shared-memory FFT path (power-of-two sides <= 128): non-square, multi-channel,
+                                   # smallest side, and (batch 3) an image with zero difference -> clamp_min branch
+                                   (2, 3, 64, 128), (3, 2, 16, 8), (3, 1, 2, 4), (5, 1, 128, 32)])
 def test_focal_frequency_loss_core(shape, alpha):
-    """FocalFrequencyLoss on CUDA (rfft2 + bvae_ffl_*) against the reference composition (fft2 of both images,
-    src/training/losses.py:23-33) in fp64, values and gradient."""
+    """FocalFrequencyLoss on CUDA (shared-memory FFT kernels, or rfft2 + bvae_ffl_* for other sizes) against the
+    reference composition (fft2 of both images, src/training/losses.py:23-33) in fp64, values and gradient."""
     from training.losses import FocalFrequencyLoss
     g = torch.Generator().manual_seed(sum(shape))
     pred = torch.rand(shape, generator=g)
@@ -530,6 +533,11 @@ def test_focal_frequency_loss_core(shape, alpha):
     (got * 1.7).backward()
     assert rel_err(got, want) <= 2e-5
     assert rel_err(pd.grad / 1.7, pr.grad) <= 5e-5
+    # weight folded into the kernels
+    pd2 = pred.to(dev()).requires_grad_(True)
+    got2 = FocalFrequencyLoss(alpha=alpha)(pd2, target.to(dev()), weight=0.5)
+    got2.backward()
+    assert rel_err(got2, 0.5 * want) <= 2e-5 and rel_err(pd2.grad, 0.5 * pr.grad) <= 5e-5
 
 
 @pytest.mark.parametrize("B,size", [(2, 32), (3, 64), (5, 128)])

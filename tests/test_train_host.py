@@ -122,7 +122,7 @@ def test_sharded_checkpoints_interoperate_with_the_reference(tmp_path):
 # ------------------------------------------------------------------------------------------------
 # data parallel: gradient buckets over gloo, world_size 2
 # ------------------------------------------------------------------------------------------------
-def _dp_worker(rank, world, port, out):
+def _dp_worker(rank, world, port, out, mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -136,7 +136,7 @@ def _dp_worker(rank, world, port, out):
         buckets = backward_ready_buckets(model)
         assert sorted(n for b in buckets for n in b) == sorted(names) and len(buckets) == 4
         assert buckets[0][0].startswith("final_conv") and buckets[-1][-1].startswith("encoder.0")
-        eng = TrainEngine(model, lr=1e-3, clip=3.0)                 # flat buffers + hooks + bucket plan (CPU tensors)
+        eng = TrainEngine(model, lr=1e-3, clip=3.0, dp_mode=mode)   # flat buffers + hooks + bucket plan (CPU tensors)
         assert eng.world == world
         # parameters now live in the flat buffer; every gradient slot is a view of flat_g
         for n, p in model.named_parameters():
@@ -147,7 +147,8 @@ def _dp_worker(rank, world, port, out):
         coef = {n: float(i + 1) for i, n in enumerate(names)}
         loss = sum(((rank + 1) * coef[n] * p).sum() for n, p in model.named_parameters())
         loss.backward()
-        assert all(c == 0 for c in eng._pending) and len(eng._works) == 4
+        # "buckets": four all-reduces were launched from the hooks; "single": none yet, finish_reduce() issues the one
+        assert all(c == 0 for c in eng._pending) and len(eng._works) == (4 if mode == "buckets" else 0)
         eng.finish_reduce()
         total = sum(r + 1 for r in range(world))
         for n, p in model.named_parameters():
@@ -160,11 +161,13 @@ def _dp_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_gradient_buckets_all_reduce_over_two_gloo_ranks():
+@pytest.mark.parametrize("mode", ["single", "buckets"])
+def test_gradient_all_reduce_over_two_gloo_ranks(mode, monkeypatch):
+    monkeypatch.delenv("BVAE_DP_MODE", raising=False)
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
-    port = 29500 + (os.getpid() % 400)
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, out)) for r in range(2)]
+    port = 29500 + (os.getpid() % 400) + (7 if mode == "single" else 0)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, out, mode)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
