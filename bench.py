@@ -488,9 +488,40 @@ def cuda_main(args):
     for i in range(warm):
         train_step(xs[i % n_batches])
 
-    # ---- data-parallel consistency: after warm-up every rank must hold bit-identical parameters
+    # ---- data-parallel consistency: the exchange sums exactly, and after warm-up every rank must hold bit-identical
+    #      parameters
     dp_check = None
     if world > 1:
+        torch.cuda.synchronize()
+        # the gradient exchange on a known pattern: rank r contributes (r + 1) * (i mod 251) -> sum = W (W + 1) / 2 * (i mod 251)
+        saved_g = engine.flat_g.clone()
+        pat = (torch.arange(engine.numel, device=dev) % 251).float()
+        engine.flat_g.copy_(pat * (rank + 1))
+        if engine.dp_mode == "nvls":
+            engine._nvls_all_reduce()
+        else:
+            dist.all_reduce(engine.flat_g)
+        torch.cuda.synchronize()
+        exact = bool(torch.equal(engine.flat_g, pat * (world * (world + 1) // 2)))
+        ex = torch.tensor([1.0 if exact else 0.0], device=dev)
+        dist.all_reduce(ex, op=dist.ReduceOp.MIN)
+        # the exchange alone, device-timed (10 launches between two events, max over ranks)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(10):
+            if engine.dp_mode == "nvls":
+                engine._nvls_all_reduce()
+            else:
+                dist.all_reduce(engine.flat_g)
+        ev1.record()
+        torch.cuda.synchronize()
+        xus = torch.tensor([ev0.elapsed_time(ev1) * 100.0], device=dev)
+        dist.all_reduce(xus, op=dist.ReduceOp.MAX)
+        exchange_us = float(xus[0])
+        engine.flat_g.copy_(saved_g)
+        del saved_g, pat
         torch.cuda.synchronize()
         ck = torch.stack([engine.flat_p.double().sum(), engine.flat_p.view(torch.int32).long().sum().double()])
         lo, hi = ck.clone(), ck.clone()
@@ -499,6 +530,9 @@ def cuda_main(args):
         dp_check = {"param_sum_min": float(lo[0]), "param_sum_max": float(hi[0]),
                     "param_bits_min": float(lo[1]), "param_bits_max": float(hi[1]),
                     "identical": bool(torch.equal(lo, hi)), "after_steps": warm,
+                    "exchange": engine.dp_mode, "exchange_sums_exactly": bool(ex[0] > 0.5),
+                    "exchange_timeouts": engine.nvls_status(), "exchange_us_isolated": exchange_us,
+                    "exchange_bytes": engine.numel * 4,
                     "what": "sum and int32-bit-pattern sum of every rank's flat fp32 parameter buffer, all-reduce MIN vs MAX"}
 
     # ---- (1) device-resident throughput
@@ -562,7 +596,7 @@ def cuda_main(args):
         "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": config_key(workload, cfg, batch),
-        "global_batch": batch * world, "parallelism": f"dp{world}",
+        "global_batch": batch * world, "parallelism": f"dp{world}" + (f" ({engine.dp_mode} gradient exchange)" if world > 1 else ""),
         "launch": "eager" if graphed is None else "whole step captured in one CUDA graph",
         "l2": f"no explicit flush: {n_batches} rotating input batches and every step streams its activations "
               f"(y + out of every block, fwd and bwd) through HBM",

@@ -23,6 +23,7 @@ LOCAL batch on each rank, i.e. DistributedDataParallel semantics.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -65,21 +66,30 @@ class TrainEngine:
                  decoupled_wd: bool = False, clip: float = 0.0, process_group=None, reduce_dtype=torch.float32,
                  dp_mode: Optional[str] = None):
         """``dp_mode``: how the gradient exchange is issued when world > 1 --
-        "single": ONE all-reduce of the whole flat gradient buffer after backward (default);
+        "nvls": this repo's own all-reduce kernel (csrc/allreduce_nvls.cu) on the flat gradient buffer, which then lives in
+                symmetric memory bound to an NVSwitch multicast object (in-switch fp32 reduction): ONE launch after
+                backward, 138 us for 38 MB on 8 x B200 against NCCL's 184 us (default on CUDA when the group supports
+                multicast, else "single").  BVAE_NVLS_OVERLAP=1 issues it per backward-ready bucket on a side stream
+                instead -- measured SLOWER (1.70 vs 1.60 ms at 2 GPUs): a forked CUDA graph loses more in kernel-to-kernel
+                latency than the hidden exchange gains, as round 1's side-stream experiment found;
+        "single": ONE NCCL all-reduce of the whole flat gradient buffer after backward;
         "buckets": the four backward-ready buckets, each launched from a post-accumulate hook under the rest of backward.
         Measured on 8 x B200 (profiles/): the persistent convolution kernels own every SM, so NCCL's CTAs only run at
         kernel boundaries -- the bucketed launches cost more in disturbed kernels and launch latency than the exposed
         ~100 us of one 38 MB NVLS all-reduce.  BVAE_DP_MODE overrides."""
         import os
-        self.dp_mode = os.environ.get("BVAE_DP_MODE", dp_mode or "single")
-        if self.dp_mode not in ("single", "buckets"):
-            raise ValueError(f"dp_mode '{self.dp_mode}' (single | buckets)")
+        self.dp_mode = os.environ.get("BVAE_DP_MODE", dp_mode or "auto")
+        if self.dp_mode not in ("auto", "nvls", "single", "buckets"):
+            raise ValueError(f"dp_mode '{self.dp_mode}' (auto | nvls | single | buckets)")
+        self._nvls = None
         self.model = model
         self.lr, self.betas, self.eps = float(lr), tuple(betas), float(eps)
         self.weight_decay, self.decoupled_wd, self.clip = float(weight_decay), bool(decoupled_wd), float(clip)
         self.step_count = 0
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if os.environ.get("BVAE_DP_REDUCE_DTYPE", "") == "bf16":      # opt-in: halves the bytes, rounds the summands
+            reduce_dtype = torch.bfloat16
         self.reduce_dtype = reduce_dtype
         named = dict(model.named_parameters())
         self._named = named
@@ -93,9 +103,11 @@ class TrainEngine:
         for s in sizes:
             offs.append(off)
             off += (s + 3) // 4 * 4
+        if self.world > 1:
+            off = (off + 4 * self.world * 128 - 1) // (4 * self.world * 128) * (4 * self.world * 128)   # even rank slices
         self.numel = off
         self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = self._alloc_grad_buffer(off, dev)
         self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(off, dtype=torch.float32, device=dev)
         self.slots = {}
@@ -130,6 +142,78 @@ class TrainEngine:
             model.invalidate_packs()
         self.last_grad_norm = None
 
+    # ------------------------------------------------------------------ NVLS exchange (symmetric gradient buffer)
+    NVLS_BLOCKS = int(__import__("os").environ.get("BVAE_NVLS_BLOCKS", "64"))   # same on every rank
+
+    def _alloc_grad_buffer(self, n, dev):
+        """The flat gradient buffer.  With world > 1 on CUDA it is allocated as symmetric memory and bound to the group's
+        NVSwitch multicast object (torch.distributed._symmetric_memory does the VMM / fabric-handle plumbing); the
+        exchange is then csrc/allreduce_nvls.cu.  Anything missing (CPU / gloo, no multicast) -> plain memory + NCCL."""
+        want = self.dp_mode in ("auto", "nvls")
+        if not (want and self.world > 1 and dev.type == "cuda"):
+            if self.dp_mode in ("auto", "nvls"):
+                if self.dp_mode == "nvls" and self.world > 1:
+                    raise RuntimeError("dp_mode 'nvls' needs CUDA tensors")
+                self.dp_mode = "single"
+            return torch.zeros(n, dtype=torch.float32, device=dev)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            gname = group.group_name
+            if hasattr(symm, "enable_symm_mem_for_group"):
+                try:
+                    symm.enable_symm_mem_for_group(gname)
+                except Exception:  # noqa: BLE001  (newer torch enables groups implicitly)
+                    pass
+            g = symm.empty(n, dtype=torch.float32, device=dev)
+            g.zero_()
+            hdl = symm.rendezvous(g, group=gname)
+            if not hdl.multicast_ptr:
+                raise RuntimeError("the group has no NVLS multicast support")
+            nflags = query("bvae_allreduce_nvls_flag_count", self.NVLS_BLOCKS, self.world)
+            flags = symm.empty(nflags, dtype=torch.int32, device=dev)
+            flags.zero_()
+            fh = symm.rendezvous(flags, group=gname)
+            state = torch.zeros(query("bvae_allreduce_nvls_state_bytes"), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.pg)                          # every rank's flags are zero before the first exchange
+            self._nvls = {"hdl": hdl, "fh": fh, "flags": flags, "state": state, "mc": int(hdl.multicast_ptr),
+                          "flag_ptrs": int(fh.buffer_ptrs_dev), "n": n, "stream": torch.cuda.Stream(device=dev),
+                          "overlap": os.environ.get("BVAE_NVLS_OVERLAP", "0") == "1", "launched": 0}
+            self.dp_mode = "nvls"
+            return g
+        except Exception as e:  # noqa: BLE001
+            if self.dp_mode == "nvls":
+                raise
+            import warnings
+            warnings.warn(f"NVLS gradient exchange unavailable ({e}); using NCCL")
+            self.dp_mode = "single"
+            return torch.zeros(n, dtype=torch.float32, device=dev)
+
+    def _nvls_all_reduce(self, lo=0, hi=None):
+        """Sum floats [lo, hi) of the gradient buffer over the ranks, on the current stream."""
+        nv = self._nvls
+        hi = nv["n"] if hi is None else hi
+        call("bvae_allreduce_nvls", nv["mc"] + 4 * lo, hi - lo, nv["flag_ptrs"], nv["state"].data_ptr(),
+             dist.get_rank(self.pg), self.world, self.NVLS_BLOCKS, torch.cuda.current_stream().cuda_stream)
+
+    def _launch_reduce_nvls(self, bi):
+        """Bucket ``bi`` is complete on the current stream: exchange it on the side stream (fork; finish_reduce joins)."""
+        nv = self._nvls
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        side = nv["stream"]
+        side.wait_event(ready)
+        lo, hi = self.bucket_ranges[bi]
+        with torch.cuda.stream(side):
+            self._nvls_all_reduce(lo, hi)
+        nv["launched"] += 1
+
+    def nvls_status(self) -> int:
+        """0, or 1 when an exchange timed out waiting for a peer (reading it syncs)."""
+        return 0 if self._nvls is None else int(self._nvls["state"][8:12].view(torch.int32)[0])
+
     # ------------------------------------------------------------------ backward-side plumbing
     def _make_hook(self, name):
         view = self.slots[name][2]
@@ -141,8 +225,11 @@ class TrainEngine:
                 view.copy_(g)                                  # autograd cloned or accumulated elsewhere
                 p.grad = view
             self._pending[bi] -= 1
-            if self._pending[bi] == 0 and self.world > 1 and self.dp_mode == "buckets":
-                self._launch_reduce(bi)
+            if self._pending[bi] == 0 and self.world > 1:
+                if self.dp_mode == "buckets":
+                    self._launch_reduce(bi)
+                elif self.dp_mode == "nvls" and self._nvls["overlap"]:
+                    self._launch_reduce_nvls(bi)
         return hook
 
     def _launch_reduce(self, bi):
@@ -165,12 +252,29 @@ class TrainEngine:
             p.grad = None
         self._pending = [len(b) for b in self.bucket_names]
         self._works = []
+        if self._nvls is not None:
+            self._nvls["launched"] = 0
 
     def finish_reduce(self):
         """Wait for the bucket all-reduces (stream-side) and restore fp32 gradients; in "single" mode issue the one
         all-reduce of the whole gradient buffer here (backward has been enqueued in full at this point)."""
-        if self.world > 1 and self.dp_mode == "single":
+        if self.world > 1 and self.dp_mode in ("single", "nvls"):
+            import os
+            if os.environ.get("BVAE_DP_SKIP_ALL") == "1":       # dev knob: the multi-rank step without its collective
+                return
             self._zero_unused()                                 # stale slots must not be summed into other ranks' gradients
+            if self.dp_mode == "nvls":
+                nv = self._nvls
+                if nv["overlap"] and nv["launched"] > 0:
+                    # join: every bucket's exchange was issued on the side stream as its gradients completed
+                    done = torch.cuda.Event()
+                    done.record(nv["stream"])
+                    torch.cuda.current_stream().wait_event(done)
+                    assert nv["launched"] == len(self.bucket_names), "a gradient bucket never completed"
+                    nv["launched"] = 0
+                else:
+                    self._nvls_all_reduce()
+                return
             buf = self.flat_g
             if self.reduce_dtype == torch.float32:
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)

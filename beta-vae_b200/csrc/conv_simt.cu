@@ -363,55 +363,68 @@ __global__ void __launch_bounds__(256)
 }
 
 // dw[co][ci][t] = sum_split part[split][t][ci][co];  dbias[co] = sum_split bpart[split][co]
-// Many splits (the halo wgrad kernel uses up to one per SM): a CTA of 1024 threads = 64 float4 lanes x 16 split
-// groups covers 256 consecutive elements; every thread keeps four 16-byte loads in flight; fixed-order combine in
-// shared memory (deterministic).  Requires total % 4 == 0 (Cout % 4 == 0).
-__global__ void __launch_bounds__(1024)
+// A thread owns one float4 (four consecutive co) of the output and a share of the splits: thread (e, g) of a 256-thread
+// CTA sums splits g, g + G, ... of element e with four independent 16-byte loads in flight, the G group partials are
+// combined in fixed order through shared memory (deterministic), and group 0 scatters the four values into the
+// reference layout.  G (1..16, power of two) is chosen on the host so that elements x G fills the machine whether the
+// layer has 9K elements and 147 splits (dec3) or 295K elements and 4 splits (dec0).  The round-1 kernel (1024 threads,
+// always 16 groups, two barriers per 256 elements) spent its time in barriers: 16 us for 21 MB of L2-resident partials.
+// Requires Cout % 4 == 0.
+__global__ void __launch_bounds__(256)
     conv_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart, float* __restrict__ dw,
-                             float* __restrict__ dbias, int Cin, int Cout, int splits, int bsplits) {
-  __shared__ float4 sm[16][64];
+                             float* __restrict__ dbias, int Cin, int Cout, int splits, int bsplits, int G) {
+  __shared__ float4 sm[256];
   const long long total = 9LL * Cin * Cout;
-  const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  const long long nblk = (total + 255) / 256;
-  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const long long i = blk * 256 + 4 * e;
-    float4 acc[4];
+  const int E = 256 / G;                         // elements (float4) per CTA
+  const int e = threadIdx.x % E, g = threadIdx.x / E;
+  const long long q = (long long)blockIdx.x * E + e;      // float4 index
+  const long long i = 4 * q;
+  const bool live = i < total;
+  float4 acc[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < total) {
-      int s = grp;
-      for (; s + 48 < splits; s += 64) {
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const float* src = part + i;
+    int s = g;
+    for (; s + 3 * G < splits; s += 4 * G) {
+      float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 v = *reinterpret_cast<const float4*>(part + (size_t)(s + 16 * u) * total + i);
-          acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
-        }
-      }
-      for (; s < splits; s += 16) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)s * total + i);
-        acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(src + (size_t)(s + u * G) * total);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
       }
     }
-    sm[grp][e] = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
-                             (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
-    __syncthreads();
-    if (grp < 4 && i < total) {   // thread (grp, e) finishes component `grp` of lane e's float4
-      float v = 0.f;
-#pragma unroll
-      for (int g = 0; g < 16; ++g) v += reinterpret_cast<const float*>(&sm[g][e])[grp];
-      const long long idx = i + grp;
-      const int co = (int)(idx % Cout);
-      const int ci = (int)((idx / Cout) % Cin);
-      const int t = (int)(idx / ((long long)Cout * Cin));
-      dw[((size_t)co * Cin + ci) * 9 + t] = v;
+    for (; s < splits; s += G) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * total);
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
     }
+  }
+  float4 r = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                         (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  if (G > 1) {
+    sm[threadIdx.x] = r;
     __syncthreads();
+    if (g == 0) {
+      for (int k = 1; k < G; ++k) {
+        const float4 o = sm[k * E + e];
+        r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+      }
+    }
+  }
+  if (g == 0 && live) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int t = (int)(i / ((long long)Cout * Cin));
+    float* o = dw + ((size_t)co * Cin + ci) * 9 + t;
+    const size_t cs = (size_t)Cin * 9;
+    o[0] = r.x; o[cs] = r.y; o[2 * cs] = r.z; o[3 * cs] = r.w;
   }
   if (dbias && blockIdx.x == 0) {
     for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-      float acc = 0.f;
-      for (int s = 0; s < bsplits; ++s) acc += bpart[(size_t)s * Cout + co];
-      dbias[co] = acc;
+      float a = 0.f;
+      for (int s = 0; s < bsplits; ++s) a += bpart[(size_t)s * Cout + co];
+      dbias[co] = a;
     }
   }
 }
@@ -419,10 +432,14 @@ __global__ void __launch_bounds__(1024)
 static int launch_wgrad_reduce(const float* part, const float* bpart, float* dw, float* dbias, int Cin, int Cout,
                                int splits, int bsplits, cudaStream_t st) {
   const long long total = 9LL * Cin * Cout + Cout;
-  if (splits >= 8 && Cout % 4 == 0) {
-    long long blocks = (total - Cout + 255) / 256;
-    if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
-    conv_wgrad_reduce_kernel<<<(int)blocks, 1024, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, splits, bsplits);
+  if (Cout % 4 == 0) {
+    const long long elems = (total - Cout) / 4;
+    int G = 1;
+    // enough threads (>= ~8 warps per scheduler-slot across the chip) while every group still has >= 4 splits to sum
+    while (G < 16 && elems * G < 64LL * 1024 * 2 && splits / (2 * G) >= 4) G *= 2;
+    const int E = 256 / G;
+    const long long blocks = (elems + E - 1) / E;
+    conv_wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(part, bpart, dw, dbias, Cin, Cout, splits, bsplits, G);
   } else {
     long long blocks = (total + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();

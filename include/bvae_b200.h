@@ -266,6 +266,21 @@ int bvae_loss_combine_fwd(const float* recon_base, const float* recon_lpips, con
                           const float* kl_scalars, float* out6, bvae_stream_t stream);
 int bvae_loss_combine_bwd(const float* g_total, const float* g_recon, float* g5, bvae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange: in-place sum of a symmetric fp32 buffer over the ranks of one node
+ * through the NVSwitch multicast object it is bound to (multimem.ld_reduce / multimem.st; one kernel per rank).
+ *   mc_ptr     multicast address of the first float of the range (16-byte aligned);  n floats, a multiple of 4
+ *   flag_ptrs  DEVICE array of `world` pointers: rank q's symmetric flag buffer (bvae_allreduce_nvls_flag_count uint32,
+ *              zeroed once) as mapped on this device;  state: bvae_allreduce_nvls_state_bytes() of zeroed device memory
+ * Every rank launches it once per exchange (same range, same nblocks, same order of exchanges); CUDA-graph replayable.
+ * No shared memory, 512-thread CTAs: it co-resides with the persistent convolution kernels, so the engine runs it per
+ * gradient bucket on a side stream under the rest of backward.
+ * ---------------------------------------------------------------------------------------- */
+size_t bvae_allreduce_nvls_state_bytes(void);
+size_t bvae_allreduce_nvls_flag_count(int nblocks, int world);
+int bvae_allreduce_nvls(void* mc_ptr, size_t n, void* flag_ptrs, void* state, int rank, int world, int nblocks,
+                        bvae_stream_t stream);
+
 /* Input pipeline: uint8 image bytes -> fp32 in [0, 1], dst[i] = float(src[i]) / 255 with IEEE division -- the values
  * torchvision's ToTensor produces from the dataset's PNGs (datautils.py:59-65), so shipping bytes over PCIe and
  * converting on the device is bit-identical to shipping ToTensor's floats.  n = element count; 16-byte aligned. */
