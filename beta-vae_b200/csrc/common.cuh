@@ -68,6 +68,11 @@ struct Vec16<float> {
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  // raw 16-byte load / unpack, split so a loop can put several loads in flight before it touches the data
+  __device__ static __forceinline__ uint4 load_raw(const float* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(const uint4& t) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
   __device__ __forceinline__ void store(float* p) const {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -76,8 +81,9 @@ template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
   float v[8];
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
-    uint4 t = *reinterpret_cast<const uint4*>(p);
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { unpack(*reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(const uint4& t) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

@@ -495,8 +495,13 @@ struct FinalGsParams {
   int loss_type;
 };
 
+// 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 and 6..9 two epilogue groups that take alternate
+// tiles (group = accumulator / G buffer): the stencil + sigmoid + loss epilogue of one tile (~1500 cycles) is longer
+// than its eight MMAs, so with one group the kernel was epilogue-bound (28 us for a 67 MB read).
+static constexpr int FG_THREADS = 320;
+
 template <int N>
-__global__ void __launch_bounds__(HL_THREADS, 1)
+__global__ void __launch_bounds__(FG_THREADS, 1)
     finalconv_gs_kernel(const __grid_constant__ HaloMaps maps, const FinalGsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -592,7 +597,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter of this warp
+    const int group = (warp - 2) >> 2;      // epilogue group 0 / 1 = accumulator buffer = G buffer
     const int r = q * 32 + lane;            // TMEM lane = halo row (first MMA) / halo row - 52 (second); also the output pixel
     const int hl = r / HL_TW, wl = r % HL_TW;
     const int nt = p.nt;
@@ -602,6 +608,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
 #pragma unroll
     for (int co = 0; co < 3; ++co) bias_r[co] = (p.bias && co < p.Co) ? p.bias[co] : 0.f;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      if ((int)(iu & 1u) != group) continue;
       int mt = u;
       const int w0 = (mt % p.tiles_w) * HL_TW;
       mt /= p.tiles_w;
@@ -645,7 +652,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);          // accumulators are in registers / shared memory now
-      asm volatile("bar.sync 1, 128;" ::: "memory");        // G of this tile complete (epilogue warps only)
+      named_bar_sync(1 + group, 128);                       // G of this tile complete (this epilogue group only)
 #pragma unroll
       for (int co = 0; co < 3; ++co) {
         if (co >= p.Co) break;
@@ -656,10 +663,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
         p.recon[o0 + (size_t)co * plane] = rr;
         if (p.target) lsum += final_elem_loss(rr, tgt[co], p.loss_type);
       }
+      named_bar_sync(1 + group, 128);                       // everyone has read G before the group's next tile overwrites it
     }
     if (p.lpart) {
       const double s = warp_sum((double)lsum);
-      if (lane == 0) p.lpart[blockIdx.x * 4 + q] = s;
+      if (lane == 0) p.lpart[blockIdx.x * 8 + (warp - 2)] = s;
     }
   }
   tc_fence_before();
@@ -717,9 +725,9 @@ int conv_halo_final_fwd(const void* h, const void* wg, const float* bias, const 
   auto kern = N == 16 ? finalconv_gs_kernel<16> : finalconv_gs_kernel<32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX);
   if (e != cudaSuccess) return cuda_fail(e, "conv_halo_final: cudaFuncSetAttribute");
-  kern<<<grid, HL_THREADS, smem, st>>>(maps, p);
+  kern<<<grid, FG_THREADS, smem, st>>>(maps, p);
   BVAE_LAUNCH_CHECK("finalconv_gs");
-  *n_lpart = grid * 4;
+  *n_lpart = grid * 8;
   return BVAE_OK;
 }
 

@@ -277,7 +277,7 @@ static FinalWs final_ws_carve(void* base, int B, int H, int W, int C, int Co) {
     off += align_up(bytes, 256);
     return r;
   };
-  w.lpart = reinterpret_cast<double*>(take((size_t)kFcMaxCtas * sizeof(double)));
+  w.lpart = reinterpret_cast<double*>(take((size_t)(kFcMaxCtas > 8 * 148 ? kFcMaxCtas : 8 * 148) * sizeof(double)));   // tcgen05 path: 8 epilogue warps per CTA
   w.dlogit = reinterpret_cast<float*>(take((size_t)B * Co * H * W * sizeof(float)));
   w.wpart = reinterpret_cast<float*>(take((size_t)kFcMaxCtas * Co * 9 * C * sizeof(float)));
   w.bpart = reinterpret_cast<float*>(take((size_t)kFcMaxCtas * Co * sizeof(float)));

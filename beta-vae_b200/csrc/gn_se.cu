@@ -146,10 +146,9 @@ __global__ void __launch_bounds__(kGnThreads)
     sx[i] = 0.f;
   }
   const T* base = y + ((size_t)b * P) * C + (size_t)col * V;
-#pragma unroll 4
-  for (int p = p0 + row; row < rows && p < p1; p += rows) {
+  auto accumulate = [&](const uint4& raw) {
     Vec16<T> v;
-    v.load(base + (size_t)p * C);
+    v.unpack(raw);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float vm = v.v[i] - mean;
@@ -157,6 +156,17 @@ __global__ void __launch_bounds__(kGnThreads)
       cnt[i] += pos ? 1.f : 0.f;
       sx[i] += pos ? vm : 0.f;
     }
+  };
+  if (row < rows) {
+    int p = p0 + row;
+    for (; p + 3 * rows < p1; p += 4 * rows) {     // four independent 16-byte loads in flight per thread
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = Vec16<T>::load_raw(base + (size_t)(p + u * rows) * C);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) accumulate(raw[u]);
+    }
+    for (; p < p1; p += rows) accumulate(Vec16<T>::load_raw(base + (size_t)p * C));
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) sx[i] *= rstd;
@@ -373,11 +383,10 @@ __global__ void __launch_bounds__(kGnThreads)
     a2[i] = 0.f;
   }
   const size_t off = ((size_t)b * P) * C + (size_t)col * V;
-#pragma unroll 2
-  for (int p = p0 + row; row < rows && p < p1; p += rows) {
+  auto accumulate = [&](const uint4& yraw, const uint4& draw) {
     Vec16<T> v, d;
-    v.load(y + off + (size_t)p * C);
-    d.load(dout + off + (size_t)p * C);
+    v.unpack(yraw);
+    d.unpack(draw);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float vm = v.v[i] - mean;
@@ -385,6 +394,21 @@ __global__ void __launch_bounds__(kGnThreads)
       a1[i] += dm;
       a2[i] = fmaf(dm, vm, a2[i]);
     }
+  };
+  if (row < rows) {
+    int p = p0 + row;
+    for (; p + 3 * rows < p1; p += 4 * rows) {     // eight independent 16-byte loads in flight per thread
+      uint4 yr[4], dr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        yr[u] = Vec16<T>::load_raw(y + off + (size_t)(p + u * rows) * C);
+        dr[u] = Vec16<T>::load_raw(dout + off + (size_t)(p + u * rows) * C);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) accumulate(yr[u], dr[u]);
+    }
+    for (; p < p1; p += rows)
+      accumulate(Vec16<T>::load_raw(y + off + (size_t)p * C), Vec16<T>::load_raw(dout + off + (size_t)p * C));
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) a2[i] *= rstd;
