@@ -784,6 +784,8 @@ extern "C" int bvae_conv3x3_wgrad(const void* x, const void* dy, float* dw, floa
     float* bpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
     const int rc = conv_tc_wgrad(x, dy, part, dbias ? bpart : nullptr, pl, B, H, W, Cin, Cout, stride, st);
     if (rc != BVAE_OK) return rc;
+    if (conv_tc_wgrad_tile_partials(H, W, Cin, Cout, stride))
+      return conv_tc_wgrad_tile_reduce(part, dw, dbias, pl, Cin, Cout, stride, st);
     return launch_wgrad_reduce(part, bpart, dw, dbias, Cin, Cout, pl.splits, pl.bias_chunks, st);
   }
   {

@@ -65,12 +65,18 @@ struct WgradTcPlan {
   int bn, slots, groups;           // co tile, accumulator slots per CTA, row-block groups
   int tiles_total, tiles_per_split, splits;
   int bias_chunks, bias_pix_per_chunk;
-  size_t part_bytes, bpart_bytes;  // workspace: partial dW [split][9][Cin][Cout], partial db [chunk][Cout]
+  size_t part_bytes, bpart_bytes;  // workspace: partial dW [split][9][Cin][Cout] (or tile order), partial db [chunk][Cout]
 };
 bool conv_tc_wgrad_supported(int H, int W, int Cin, int Cout, int stride);
 WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int stride);
 int conv_tc_wgrad(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
                   int W, int Cin, int Cout, int stride, cudaStream_t st);
+
+// true: conv_tc_wgrad leaves its partials in accumulator-tile order (bias sums included); reduce them with
+// conv_tc_wgrad_tile_reduce instead of the [split][tap][Cin][Cout] reduce of conv_simt.cu
+bool conv_tc_wgrad_tile_partials(int H, int W, int Cin, int Cout, int stride);
+int conv_tc_wgrad_tile_reduce(const float* part, float* dw, float* dbias, const WgradTcPlan& pl, int Cin, int Cout, int stride,
+                              cudaStream_t st);
 
 // ---- stride-2 dgrad, halo formulation (conv_tc_s2dgrad.cu): H, W = extent of dx; N = Cin (dx), K = Cout (dy) ----
 bool conv_s2_dgrad_halo_supported(int H, int W, int N, int K);

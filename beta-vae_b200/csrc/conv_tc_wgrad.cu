@@ -196,10 +196,8 @@ struct WgHaloParams {
   uint32_t stage_bytes;     // nplanes * slot_bytes + dy_bytes
   uint32_t sbo;             // bytes between 8-pixel atoms of a window = one buffer row
   uint32_t win[10];         // byte offset of accumulator-slot position q's window inside a stage (q = 2*rb + half)
-  int tap[10];              // weight tap (r*3+s) held at position q; position 9 = the ones block (bias gradient)
   uint32_t ones_off, bar_off;
-  float* part;   // [split][9][Cin][Cout]
-  float* bpart;  // [split][Cout] or null
+  float* part;   // [split][block][rb 5][column group 16][row 128][4]: the accumulators as they sit in TMEM
 };
 struct WgHaloMaps {
   CUtensorMap x[4], dy;
@@ -312,35 +310,100 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     if (leader) umma_commit(accum_bar);
     __syncwarp();
   } else {
+    // Partials leave the CTA in the accumulators' own shape -- [rb 5][column group 16][row 128][4 floats], 160 KB per
+    // CTA -- so that a warp's store instruction covers 32 consecutive rows x 16 bytes = one contiguous 512-byte run.
+    // (In the reference layout [tap][ci][co] every lane wrote into another 256-byte row: 32 sectors per instruction,
+    // ~5 us of un-overlapped stores at the end of every launch.)  conv_wgrad_halo_reduce_kernel undoes the permutation.
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;  // accumulator row: slot half (m / 64), input channel (m % 64)
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    float4* tile = reinterpret_cast<float4*>(p.part) + ((size_t)split * gridDim.x + blockIdx.x) * (5 * 16 * 128);
 #pragma unroll 1
     for (int rb = 0; rb < 5; ++rb) {
-      const int pos = 2 * rb + (m >> 6);
-      float* out = nullptr;
-      if (pos < 9)
-        out = p.part + (((size_t)split * 9 + p.tap[pos]) * p.Cin + (size_t)cc * 64 + (m & 63)) * p.Cout + (size_t)cb * 64;
-      else if (m == 64 && cc == 0 && p.bpart)
-        out = p.bpart + (size_t)split * p.Cout + (size_t)cb * 64;   // ones-row: sum over pixels of dy
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(rb * 64);
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        if (out) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(out + c + g * 4) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        }
+        for (int g = 0; g < 8; ++g)
+          tile[((size_t)rb * 16 + (size_t)(c / 4 + g)) * 128 + m] =
+              make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// dw[co][ci][tap] (reference layout) and dbias from the tile-native partials of conv_wgrad_halo_kernel:
+// part[split][blk = cb * cin_chunks + cc][rb][g][m][4].  A thread owns one float4 and a share of the splits (G groups,
+// combined in fixed order through shared memory: deterministic), as in conv_wgrad_reduce_kernel (conv_simt.cu).
+struct WgTapTable {
+  int t[10];
+};
+__global__ void __launch_bounds__(256)
+    conv_wgrad_halo_reduce_kernel(const float4* __restrict__ part, float* __restrict__ dw, float* __restrict__ dbias, int Cin,
+                                  int Cout, int splits, int nblk, int cin_chunks, const WgTapTable taps, int G) {
+  __shared__ float4 sm[256];
+  const long long total4 = (long long)nblk * (5 * 16 * 128);
+  const int E = 256 / G;
+  const int e = threadIdx.x % E, g = threadIdx.x / E;
+  const long long q = (long long)blockIdx.x * E + e;
+  const bool live = q < total4;
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const float4* src = part + q;
+    int s = g;
+    for (; s + 3 * G < splits; s += 4 * G) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = src[(size_t)(s + u * G) * total4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+      }
+    }
+    for (; s < splits; s += G) {
+      const float4 v = src[(size_t)s * total4];
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+    }
+  }
+  float4 r = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                         (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  if (G > 1) {
+    sm[threadIdx.x] = r;
+    __syncthreads();
+    if (g == 0) {
+      for (int k = 1; k < G; ++k) {
+        const float4 o = sm[k * E + e];
+        r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+      }
+    }
+  }
+  if (g == 0 && live) {
+    const int m = (int)(q % 128);
+    const int gi = (int)((q / 128) % 16);
+    const int rb = (int)((q / 2048) % 5);
+    const int blk = (int)(q / 10240);
+    const int cc = blk % cin_chunks, cb = blk / cin_chunks;
+    const int pos = 2 * rb + (m >> 6);
+    const int co = cb * 64 + 4 * gi;
+    if (pos < 9) {
+      const int ci = cc * 64 + (m & 63);
+      float* o = dw + ((size_t)co * Cin + ci) * 9 + taps.t[pos];
+      const size_t cs = (size_t)Cin * 9;
+      o[0] = r.x; o[cs] = r.y; o[2 * cs] = r.z; o[3 * cs] = r.w;
+    } else if (m == 64 && cc == 0 && dbias) {     // the all-ones row: sum over pixels of dy
+      dbias[co] = r.x; dbias[co + 1] = r.y; dbias[co + 2] = r.z; dbias[co + 3] = r.w;
+    }
+  }
 }
 
 static bool wgrad_halo_ok(int H, int W, int Cin, int Cout, int stride) {
@@ -351,6 +414,28 @@ static bool wgrad_halo_ok(int H, int W, int Cin, int Cout, int stride) {
   return (stride == 1 || stride == 2) && OH % 8 == 0 && OW % 8 == 0;
 }
 static int wgrad_halo_th(int OH) { return OH % 16 == 0 ? 16 : 8; }
+// stride 2: accumulator position -> tap, sorted by window address inside the four parity planes
+static const int kWgS2TapOrder[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
+
+bool conv_tc_wgrad_tile_partials(int H, int W, int Cin, int Cout, int stride) { return wgrad_halo_ok(H, W, Cin, Cout, stride); }
+
+int conv_tc_wgrad_tile_reduce(const float* part, float* dw, float* dbias, const WgradTcPlan& pl, int Cin, int Cout, int stride,
+                              cudaStream_t st) {
+  WgTapTable taps;
+  for (int pos = 0; pos < 9; ++pos) taps.t[pos] = stride == 1 ? pos : kWgS2TapOrder[pos];
+  taps.t[9] = -1;
+  const int nblk = (Cin / 64) * (Cout / 64);
+  const long long elems = (long long)nblk * (5 * 16 * 128);
+  int G = 1;
+  // enough threads to cover the latency of the split walk while every group still has >= 4 splits to sum
+  while (G < 16 && elems * G < 64LL * 1024 * 2 && pl.splits / (2 * G) >= 4) G *= 2;
+  const int E = 256 / G;
+  const long long blocks = (elems + E - 1) / E;
+  conv_wgrad_halo_reduce_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(part), dw, dbias, Cin, Cout,
+                                                           pl.splits, nblk, Cin / 64, taps, G);
+  BVAE_LAUNCH_CHECK("conv_wgrad_halo_reduce");
+  return BVAE_OK;
+}
 
 static int conv_wgrad_halo(const void* x, const void* dy, float* part, float* bpart, const WgradTcPlan& pl, int B, int H,
                            int W, int Cin, int Cout, int stride, cudaStream_t st) {
@@ -368,14 +453,13 @@ static int conv_wgrad_halo(const void* x, const void* dy, float* part, float* bp
   p.tiles_per_split = pl.tiles_per_split;
   p.Cin = Cin; p.Cout = Cout;
   p.part = part;
-  p.bpart = bpart;
+  (void)bpart;   // the bias sums ride in the fifth accumulator
   p.dy_bytes = (uint32_t)p.th * 8 * 128;
   uint32_t bw, bh;   // plane box: pixels per row, rows
   if (stride == 1) {
     p.nplanes = 1; bw = 10; bh = (uint32_t)p.th + 2;
     for (int j = 0; j < 9; ++j) {
       p.win[j] = (uint32_t)((j / 3) * 10 + (j % 3)) * 128u;
-      p.tap[j] = j;
     }
   } else {
     p.nplanes = 4; bw = 9; bh = (uint32_t)p.th + 1;
@@ -386,17 +470,14 @@ static int conv_wgrad_halo(const void* x, const void* dy, float* part, float* bp
   p.stage_bytes = (uint32_t)p.nplanes * p.slot_bytes + p.dy_bytes;
   if (stride == 2) {
     // taps sorted by window address: plane slot q = ph*2+pw with ph = (r != 1), pw = (s != 1); row/col offset (r != 0), (s != 0)
-    static const int order[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
     for (int pos = 0; pos < 9; ++pos) {
-      const int t = order[pos], r = t / 3, s = t % 3;
+      const int t = kWgS2TapOrder[pos], r = t / 3, s = t % 3;
       const int q = (r != 1 ? 2 : 0) + (s != 1 ? 1 : 0);
       p.win[pos] = (uint32_t)q * p.slot_bytes + (uint32_t)((r != 0 ? 1 : 0) * (int)bw + (s != 0 ? 1 : 0)) * 128u;
-      p.tap[pos] = t;
       if (pos > 0) BVAE_REQUIRE(p.win[pos] > p.win[pos - 1], BVAE_ERR_UNSUPPORTED, "conv_wgrad_halo: window order");
     }
   }
   p.win[9] = 0;
-  p.tap[9] = -1;
   const size_t budget = 226 * 1024 - 1024 - 4096;
   int stages = (int)(budget / p.stage_bytes);
   p.stages = stages > 5 ? 5 : stages;
@@ -490,8 +571,9 @@ WgradTcPlan conv_tc_wgrad_plan(int B, int H, int W, int Cin, int Cout, int strid
     pl.splits = (pl.tiles_total + pl.tiles_per_split - 1) / pl.tiles_per_split;
     pl.bias_chunks = pl.splits;
     pl.bias_pix_per_chunk = 0;
-    pl.part_bytes = align_up((size_t)pl.splits * 9 * Cin * Cout * sizeof(float), 256);
-    pl.bpart_bytes = align_up((size_t)pl.splits * Cout * sizeof(float), 256);
+    // tile-native partials: [split][block][5][16][128][4] floats (the bias row lives in the fifth accumulator)
+    pl.part_bytes = align_up((size_t)pl.splits * pl.groups * (5 * 16 * 128 * 4) * sizeof(float), 256);
+    pl.bpart_bytes = 256;
     return pl;
   }
   const int OW = (W - 1) / stride + 1, OH = (H - 1) / stride + 1;
