@@ -437,12 +437,18 @@ class GraphedTrainStep:
         self._consumed = [None, None]
         self._slot = 0
 
-    def prefetch(self, x) -> "StagedBatch":
+    def prefetch(self, x, augment=None) -> "StagedBatch":
+        """Start the host->device copy of batch ``x`` on the copy stream.  ``augment`` (bvae_rt.augment.DeviceAugment)
+        is applied to uint8 batches right behind the copy, on the same stream -- the reference does this work per
+        sample in its DataLoader workers (augmentations.py:5-18)."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.engine.device)
             self._stage = {}
         if x.dtype not in self._stage:               # fp32 images, or uint8 bytes (converted on the device: x / 255)
             self._stage[x.dtype] = [torch.empty(self.x.shape, dtype=x.dtype, device=self.x.device) for _ in range(2)]
+        aug = augment is not None and x.dtype == torch.uint8
+        if aug and "aug" not in self._stage:
+            self._stage["aug"] = [torch.empty(self.x.shape, dtype=torch.uint8, device=self.x.device) for _ in range(2)]
         slot = self._slot
         self._slot ^= 1
         buf = self._stage[x.dtype][slot]
@@ -451,6 +457,8 @@ class GraphedTrainStep:
             cs.wait_event(self._consumed[slot])      # the step that read this buffer two batches ago
         with torch.cuda.stream(cs):
             buf.copy_(x, non_blocking=True)
+            if aug:
+                buf = augment(buf, out=self._stage["aug"][slot])
             ready = torch.cuda.Event()
             ready.record(cs)
         return StagedBatch(slot, buf, ready)

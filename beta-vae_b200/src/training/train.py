@@ -16,8 +16,9 @@
 
 Multi-GPU: launch one process per GPU (torchrun); every rank runs this function on its own loader shard, gradients
 are all-reduced by the engine, rank 0 logs and writes checkpoints.  Out of scope here: the PIL/torchvision dataset
-(pass any iterable of ``{"image": tensor [B,C,H,W] in [0,1], "label": ...}`` batches; without one, synthetic
-MRI-shaped batches are generated on the device), the sklearn probe metrics and the reconstruction PNG panels."""
+(pass any iterable of ``{"image": tensor [B,C,H,W], "label": ...}`` batches -- floats in [0,1] as ToTensor leaves them,
+or the sized uint8 bytes, which are augmented per cfg.augmentation and scaled on the device; without a loader,
+synthetic MRI-shaped batches are generated on the device), the sklearn probe metrics and the reconstruction PNG panels."""
 import argparse
 import math
 import os
@@ -33,6 +34,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from bvae_rt.augment import DeviceAugment
 from bvae_rt.data import synthetic_batch
 from bvae_rt.engine import GraphedTrainStep, StagedBatch, TrainEngine, cosine_lr
 from models.beta_vae import BetaVAE
@@ -109,19 +111,24 @@ def _payload(model, engine, epoch, total_steps, val_total):
     }
 
 
-def _staged_images(loader, step_fn):
+def _staged_images(loader, step_fn, augment=None):
     """The loader's image batches, one step ahead: when batch i is handed to the step, the host->device copy of batch
     i+1 is already running on the copy stream (GraphedTrainStep.prefetch).  Without a graphed step, or for batches
     that already live on the device, the tensors pass through unchanged.  A batch whose shape differs from the graph's
     static input (the last, partial batch of an epoch: the reference's DataLoader has no ``drop_last``,
-    datautils.py:78-91) is not staged either; ``train`` runs it through the un-captured step."""
+    datautils.py:78-91) is not staged either; ``train`` runs it through the un-captured step.
+    ``augment``: uint8 batches are the dataset's bytes BEFORE the train transform; they get the reference's flip /
+    rotation / brightness on the device (bvae_rt.augment).  Float batches come from a loader that already ran its own
+    transform (ToTensor is its last stage) and pass through untouched."""
     prev = None
     for batch_d in loader:
         x = batch_d["image"]
         if isinstance(x, (list, tuple)):
             x = torch.stack(x, 0)
         if step_fn is not None and not x.is_cuda and tuple(x.shape) == tuple(step_fn.x.shape):
-            x = step_fn.prefetch(x)
+            x = step_fn.prefetch(x, augment)
+        elif augment is not None and x.dtype == torch.uint8:
+            x = augment(x.to(step_fn.x.device if step_fn is not None else torch.cuda.current_device(), non_blocking=True))
         if prev is not None:
             yield prev
         prev = x
@@ -174,6 +181,8 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
     capacity_scheduler = CapacityScheduler(cfg, total_epochs=epochs)
     loss_cfg = getattr(cfg, "loss", None)
     capacity_weight_cfg = getattr(loss_cfg, "capacity_weight", None) if loss_cfg else None
+    # the reference builds its train transform from cfg.augmentation (augmentations.py:5-18); test data is never augmented
+    augment = DeviceAugment.from_config(cfg) if hasattr(cfg, "augmentation") else None
     early = EarlyStopping(patience=20)
     models_dir, run_id = cfg.paths.models_dir, cfg.paths.run_id
     best_value = None
@@ -209,7 +218,7 @@ def train(resume="none", cfg=None, train_loader=None, test_loader=None, use_grap
         running = torch.zeros(6, device=device)     # packed order: total, recon, kl, recon_ffl, recon_base, recon_lpips
         last = None
         n_batches = 0
-        for i, x in enumerate(_staged_images(train_loader, step_fn)):
+        for i, x in enumerate(_staged_images(train_loader, step_fn, augment)):
             engine.lr = _lr_at(cfg, epochs, epoch - 1, total_steps)
             full = isinstance(x, StagedBatch) or tuple(x.shape) == (batch, in_ch, size, size)
             if step_fn is not None and full:

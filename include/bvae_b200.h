@@ -286,6 +286,18 @@ int bvae_allreduce_nvls(void* mc_ptr, size_t n, void* flag_ptrs, void* state, in
  * converting on the device is bit-identical to shipping ToTensor's floats.  n = element count; 16-byte aligned. */
 int bvae_u8_to_unit_f32(const void* src, float* dst, size_t n, bvae_stream_t stream);
 
+/* Train-time augmentation of a uint8 batch [B][C][H][W] on the device: horizontal flip -> nearest-neighbour rotation
+ * about the image centre (fill 0) -> brightness, per sample -- what the reference's train transform does to each PIL
+ * image inside its DataLoader workers (src/data_processing/augmentations.py:5-18: torchvision RandomHorizontalFlip,
+ * RandomRotation(degrees), ColorJitter(brightness), followed by ToTensor), bit for bit.
+ *   params    DEVICE array [B][8] of 32-bit words per sample: {flags, a0, a1, a2, a3, a4, a5, factor(fp32 bits)};
+ *             flags bit 4 = mirror, bit 5 = apply brightness `factor`; a0..a5 = Pillow's 16.16 fixed-point inverse
+ *             affine coefficients (identity: a0 = a4 = 65536, others 0).  bvae_rt/augment.py builds them.
+ *   dst_u8    augmented bytes, or null;  dst_unit: the same pixels as fp32 v / 255 (ToTensor), or null.  Not in place.
+ * W must be a multiple of 4. */
+int bvae_augment_u8(const void* src, void* dst_u8, float* dst_unit, const void* params, int B, int C, int H, int W,
+                    bvae_stream_t stream);
+
 /* NCHW fp32 -> NHWC act dtype (RGB input path, data.grayscale: false) and back. */
 int bvae_nchw_to_nhwc(const float* x, void* y, int B, int C, int H, int W, int dtype, bvae_stream_t stream);
 

@@ -202,7 +202,8 @@ def test_train_loop_stages_batches_one_ahead():
             self.x = torch.zeros(4, 1, 8, 8)
             self.log = []
 
-        def prefetch(self, t):
+        def prefetch(self, t, augment=None):
+            assert augment is None
             self.log.append(("prefetch", int(t[0, 0, 0, 0])))
             return ("staged", int(t[0, 0, 0, 0]))
 
