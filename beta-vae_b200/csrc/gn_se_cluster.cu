@@ -27,6 +27,17 @@ namespace bvae {
 static constexpr int GC_THREADS = 512;
 static constexpr float kGcEps = 1e-5f;  // nn.GroupNorm default
 
+// dev builds (-DBVAE_GC_TIMING): cycle stamps of CTA (0, 0) at the phase boundaries, read by tools/gc_phase_times.py
+#ifdef BVAE_GC_TIMING
+__device__ long long g_gc_ts[32];
+#define GC_TS(i)                                                                      \
+  do {                                                                                \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_gc_ts[i] = clock64(); \
+  } while (0)
+#else
+#define GC_TS(i)
+#endif
+
 __device__ __forceinline__ uint32_t gc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gc_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gc_smem_u32(bar)), "r"(count));
@@ -63,53 +74,103 @@ __device__ __forceinline__ void gc_load_slice(void* dst, const void* src, uint32
   }
 }
 
-// Per-channel sums over this CTA's pixels of two per-thread accumulator sets -> out0[c], out1[c] (double, fixed order).
-// G = min(8, threads / C) threads share a channel (adjacent lanes), each summing every G-th row in double, then a
-// fixed-order shuffle combine: the one-thread-per-channel loop over up to 64 rows was a serial latency chain.
+// Per-channel sums over this CTA's pixels of two per-thread accumulator sets -> out0[c], out1[c] (fixed order).
+// Thread t holds channels (t % cv) * V .. + V of pixel rows t / cv, + rows, ...  Rows that share a warp (cv < 32) are
+// combined first with an xor butterfly in registers; the per-warp (or per-row) partials then go to shared memory as
+// 16-byte stores -- the former scalar stores at a 32-byte lane stride were 8-way bank conflicts, ~2000 cycles per
+// call -- and 2*C threads add the <= 16 partials of one output each, in double.  fp32 activations (V = 4) run the
+// butterfly in double as well: the fp32 path is held to 1e-5 of the fp32 reference, the bf16 path is not.
 template <int V>
-__device__ __forceinline__ void gc_channel_reduce(const float (&a0)[V], const float (&a1)[V], float* scratch, int C, int cv,
-                                                  int rows, float* out0, float* out1) {
-  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
-  float* s0 = scratch;
-  float* s1 = scratch + rows * C;
+__device__ __forceinline__ void gc_channel_reduce(float (&a0)[V], float (&a1)[V], float* scratch, int C, int cv, int rows,
+                                                  float* out0, float* out1) {
+  constexpr bool kPrecise = V == 4;      // fp32 activations: every combine in double (parity with the fp32 reference at 1e-5)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = threadIdx.x % cv;
+  int nparts;
+  if (cv < 32) {
+    nparts = (int)blockDim.x >> 5;
+    if (kPrecise) {
+      double d0[V], d1[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    s0[row * C + col * V + i] = a0[i];
-    s1[row * C + col * V + i] = a1[i];
-  }
-  __syncthreads();
-  int G = (int)blockDim.x / C;
-  G = G >= 8 ? 8 : (G >= 4 ? 4 : (G >= 2 ? 2 : 1));
-  if (G > rows) G = 1;
-  if (G > 1) {
-    const int c = threadIdx.x / G, g = threadIdx.x % G;
-    double a = 0.0, q = 0.0;
-    if (c < C) {
-      for (int r = g; r < rows; r += G) {
-        a += (double)s0[r * C + c];
-        q += (double)s1[r * C + c];
+      for (int i = 0; i < V; ++i) {
+        d0[i] = (double)a0[i];
+        d1[i] = (double)a1[i];
       }
-    }
-    for (int o = 1; o < G; o <<= 1) {     // all 32 lanes participate; groups are G-aligned within a warp
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (c < C && g == 0) {
-      out0[c] = (float)a;
-      out1[c] = (float)q;
+      for (int o = cv; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          d0[i] += __shfl_xor_sync(0xffffffffu, d0[i], o);
+          d1[i] += __shfl_xor_sync(0xffffffffu, d1[i], o);
+        }
+      }
+      if (lane < cv) {
+        double* p0 = reinterpret_cast<double*>(scratch) + (size_t)warp * 2 * C + col * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          p0[i] = d0[i];
+          p0[C + i] = d1[i];
+        }
+      }
+    } else {
+      for (int o = cv; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
+          a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+        }
+      }
     }
   } else {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      double a = 0.0, q = 0.0;
-      for (int r = 0; r < rows; ++r) {
-        a += (double)s0[r * C + c];
-        q += (double)s1[r * C + c];
-      }
-      out0[c] = (float)a;
-      out1[c] = (float)q;
+    nparts = rows;
+  }
+  const bool dbl = kPrecise && cv < 32;
+  if (!dbl && (cv >= 32 || lane < cv)) {
+    const int part = cv < 32 ? warp : (int)threadIdx.x / cv;
+    float* d0 = scratch + (size_t)part * 2 * C + col * V;
+    float* d1 = d0 + C;
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      *reinterpret_cast<float4*>(d0 + i) = make_float4(a0[i], a0[i + 1], a0[i + 2], a0[i + 3]);
+      *reinterpret_cast<float4*>(d1 + i) = make_float4(a1[i], a1[i + 1], a1[i + 2], a1[i + 3]);
     }
   }
   __syncthreads();
+  for (int o = threadIdx.x; o < 2 * C; o += blockDim.x) {
+    double acc = 0.0;
+    if (dbl) {
+      for (int r = 0; r < nparts; ++r) acc += reinterpret_cast<const double*>(scratch)[(size_t)r * 2 * C + o];
+    } else {
+      for (int r = 0; r < nparts; ++r) acc += (double)scratch[(size_t)r * 2 * C + o];
+    }
+    if (o < C) out0[o] = (float)acc;
+    else out1[o - C] = (float)acc;
+  }
+  __syncthreads();
+}
+
+// two block-wide double sums with one set of barriers; `red` holds 64 doubles
+__device__ __forceinline__ void gc_block_sum2(double& a, double& b, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)blockDim.x >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) {
+    red[w] = a;
+    red[32 + w] = b;
+  }
+  __syncthreads();
+  if (w == 0) {
+    double ra = lane < nw ? red[lane] : 0.0, rb = lane < nw ? red[32 + lane] : 0.0;
+    ra = warp_sum(ra);
+    rb = warp_sum(rb);
+    if (lane == 0) {
+      red[0] = ra;
+      red[32] = rb;
+    }
+  }
+  __syncthreads();
+  a = red[0];
+  b = red[32];
 }
 
 struct GcSmem {
@@ -159,18 +220,27 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   float* v_p1 = v_p0 + C;
   double* st_gather = reinterpret_cast<double*>(gsm + L.misc);          // [CS][2]
   uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + L.misc + 512);
-  __shared__ double red[32];
+  __shared__ double red[64];
 
+  GC_TS(0);
+  cluster.barrier_arrive();   // "this CTA is running"; waited on right before the first DSMEM access, free by then
   const T* src = y + ((size_t)b * P + (size_t)rank * pix) * C;
   if (threadIdx.x == 0) {
     gc_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     gc_load_slice(ys, src, slice_bytes, bar);
   }
+  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
+  float gm[V], bt[V];      // loaded now: their latency hides behind the slice's bulk copy
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    gm[i] = gamma[col * V + i];
+    bt[i] = beta[col * V + i];
+  }
   __syncthreads();         // barrier initialised before anyone waits on it
   gc_mbar_wait(bar, 0);
+  GC_TS(1);
 
-  const int col = threadIdx.x % cv, row = threadIdx.x / cv;
   // ---- 1. statistics
   float s = 0.f, ss = 0.f;
   for (int p = row; p < pix; p += rows) {
@@ -182,15 +252,17 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       ss = fmaf(v.v[i], v.v[i], ss);
     }
   }
-  const double ds = block_sum((double)s, red);
-  const double dss = block_sum((double)ss, red);
-  cluster.sync();          // every CTA of the cluster is running before the first DSMEM access (hidden behind the load)
+  double ds = (double)s, dss = (double)ss;
+  gc_block_sum2(ds, dss, red);
+  GC_TS(2);
+  cluster.barrier_wait();  // every CTA of the cluster is running before the first DSMEM access
   if (threadIdx.x < CS) {  // all-gather: my partial into slot `rank` of every CTA
     double* dst = cluster.map_shared_rank(st_gather, threadIdx.x);
     dst[2 * rank] = ds;
     dst[2 * rank + 1] = dss;
   }
   cluster.sync();
+  GC_TS(3);
   double ts = 0.0, tss = 0.0;
   for (int r = 0; r < CS; ++r) {
     ts += st_gather[2 * r];
@@ -204,11 +276,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
 
   // z = (y - mean) * (rstd * gamma) + beta  is THE pre-activation in every pass (forward and backward, both kernel
   // families): one FADD + one FFMA per element, and the relu mask z > 0 is identical everywhere.
-  float za[V], bt[V], sc[V];
+  float za[V], sc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    za[i] = rstd * gamma[col * V + i];
-    bt[i] = beta[col * V + i];
+    za[i] = rstd * gm[i];
     sc[i] = 1.f;
   }
   if (has_se) {
@@ -229,7 +300,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) sx[i] *= rstd;
+    GC_TS(4);
     gc_channel_reduce<V>(cnt, sx, scratch, C, cv, rows, v_p0, v_p1);
+    GC_TS(5);
     for (int r = 0; r < CS; ++r) {  // all-gather my [2][C] partials
       float* dst = cluster.map_shared_rank(gather, r) + (size_t)rank * 2 * C;
       for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -238,6 +311,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       }
     }
     cluster.sync();
+    GC_TS(6);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       double a = 0.0, q = 0.0;
       for (int r = 0; r < CS; ++r) {
@@ -250,6 +324,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       v_pool[c] = (gamma[c] * qf + beta[c] * af) / (float)P;   // mean over pixels of relu(gn(y))
     }
     __syncthreads();
+    GC_TS(7);
     // ---- 3. excitation.  Small SE blocks (C*R <= 4096 weights): every CTA computes all of it, no all-gather;
     //         otherwise hidden[j] for j = rank, rank + CS, ... and gate[c] for this CTA's channel slice, all-gathered.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -257,7 +332,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     const int jstep = split ? CS : 1, j0 = split ? rank : 0;
     for (int j = j0 + warp * jstep; j < R; j += nwarp * jstep) {
       float acc = 0.f;
-      for (int c = lane; c < C; c += 32) acc = fmaf(w1[(size_t)j * C + c], v_pool[c], acc);
+      const float* wr = w1 + (size_t)j * C;
+#pragma unroll 8
+      for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(wr + c), v_pool[c], acc);
       acc = warp_sum(acc);
       const float h = fmaxf(acc + b1[j], 0.f);
       if (split) {
@@ -267,6 +344,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       }
     }
     if (split) cluster.sync(); else __syncthreads();
+    GC_TS(8);
     const int cpr = split ? (C + CS - 1) / CS : C;
     const int c_lo = split ? rank * cpr : 0, c_hi = split ? min(C, (rank + 1) * cpr) : C;
     for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
@@ -276,9 +354,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
         float a4[4] = {0.f, 0.f, 0.f, 0.f};
         const float4* wq = reinterpret_cast<const float4*>(wr);
         const float4* hq = reinterpret_cast<const float4*>(v_hid);
-#pragma unroll 4
+#pragma unroll 16
         for (int j = 0; j < R / 4; ++j) {
-          const float4 w4 = wq[j], h4 = hq[j];
+          const float4 w4 = __ldg(wq + j), h4 = hq[j];
           a4[0] = fmaf(w4.x, h4.x, a4[0]);
           a4[1] = fmaf(w4.y, h4.y, a4[1]);
           a4[2] = fmaf(w4.z, h4.z, a4[2]);
@@ -296,6 +374,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       }
     }
     if (split) cluster.sync(); else __syncthreads();
+    GC_TS(9);
 #pragma unroll
     for (int i = 0; i < V; ++i) sc[i] = v_gate[col * V + i];
   }
@@ -314,6 +393,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     for (int i = 0; i < V; ++i) v.v[i] = fmaxf(fmaf(v.v[i] - mean, zs[i], bs_[i]), 0.f);
     v.store(dst + (size_t)p * C + col * V);
   }
+  GC_TS(10);
   // ---- 5. saved tensors
   if (rank == 0) {
     if (threadIdx.x == 0) {
@@ -366,8 +446,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   float* v_p1 = v_p0 + C;
   float* v_gate = v_p1 + C;
   uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + L.misc + 512);
-  __shared__ double red[32];
+  __shared__ double red[64];
 
+  GC_TS(16);
+  cluster.barrier_arrive();   // see forward
   const size_t goff = ((size_t)b * P + (size_t)rank * pix) * C;
   if (threadIdx.x == 0) {
     gc_mbar_init(bar, 1);
@@ -389,10 +471,19 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     za[i] = rstd * g[i];
     bt[i] = beta[col * V + i];
   }
-  if (has_se)
+  // this thread's first element of the per-sample vectors phase 2 and 3 read, fetched now (latency under the bulk copy)
+  float pre_cpos = 0.f, pre_spos = 0.f, pre_hid = 0.f;
+  if (has_se) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) v_gate[c] = gate_g[(size_t)b * C + c];
+    if ((int)threadIdx.x < C) {
+      pre_cpos = cpos_g[(size_t)b * C + threadIdx.x];
+      pre_spos = spos_g[(size_t)b * C + threadIdx.x];
+    }
+    if ((int)threadIdx.x < R) pre_hid = hidden_g[(size_t)b * R + threadIdx.x];
+  }
   __syncthreads();         // barrier initialised, gate staged
   gc_mbar_wait(bar, 0);
+  GC_TS(17);
 
   // ---- 1. A1[c] = sum dout*m, A2[c] = sum dout*m*xhat over this CTA's pixels
   float a1[V], a2[V];
@@ -413,8 +504,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) a2[i] *= rstd;
+  GC_TS(18);
   gc_channel_reduce<V>(a1, a2, scratch, C, cv, rows, v_p0, v_p1);
-  cluster.sync();          // every CTA of the cluster is running before the first DSMEM access (hidden behind the pass above)
+  GC_TS(19);
+  cluster.barrier_wait();  // every CTA of the cluster is running before the first DSMEM access
   for (int r = 0; r < CS; ++r) {
     float* dst = cluster.map_shared_rank(gather, r) + (size_t)rank * 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -423,6 +516,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     }
   }
   cluster.sync();
+  GC_TS(20);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int r = 0; r < CS; ++r) {
@@ -439,6 +533,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     }
   }
   __syncthreads();
+  GC_TS(21);
   // ---- 2. SE backward, split across the cluster
   if (has_se) {
     // dz1[j] = (hidden > 0) * sum_c dz2[c] W2[c][j].  W2 is [C][R]: threads run along j (coalesced rows), channel
@@ -448,21 +543,37 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     {
       const int cpr = split ? (C + CS - 1) / CS : C;
       const int c_lo = split ? rank * cpr : 0, c_hi = split ? min(C, (rank + 1) * cpr) : C;
-      const int ng = max(1, (int)blockDim.x / R);
+      // channel groups that share a warp (R < 32) combine by an xor butterfly, the rest through shared memory: the
+      // former one-thread-per-j loop over up to 64 group partials was a serial chain of double adds
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (int)blockDim.x >> 5;
+      int RP = 1;
+      while (RP < R) RP <<= 1;                               // threads per channel group
+      const int ng = max(1, (int)blockDim.x / RP);
+      const int jj = threadIdx.x % RP, cgp = threadIdx.x / RP;
       float part = 0.f;
-      const int jj = threadIdx.x % R, cgp = threadIdx.x / R;
-      if (cgp < ng)
-        for (int c = c_lo + cgp; c < c_hi; c += ng) part = fmaf(v_dz2[c], w2[(size_t)c * R + jj], part);
-      if (cgp < ng) scratch[cgp * R + jj] = part;
+      if (cgp < ng && jj < R) {
+        const float* wp = w2 + jj;
+#pragma unroll 8
+        for (int c = c_lo + cgp; c < c_hi; c += ng) part = fmaf(v_dz2[c], __ldg(wp + (size_t)c * R), part);
+      }
+      int nparts;
+      if (RP < 32) {
+        for (int o = RP; o < 32; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        nparts = nwarp;
+        if (lane < RP && jj < R) scratch[warp * R + jj] = part;
+      } else {
+        nparts = ng;
+        if (cgp < ng && jj < R) scratch[cgp * R + jj] = part;
+      }
       __syncthreads();
       if ((int)threadIdx.x < R) {
         double acc = 0.0;   // signed terms that cancel: combine the partials in double
-        for (int q = 0; q < ng; ++q) acc += (double)scratch[q * R + threadIdx.x];
+        for (int q = 0; q < nparts; ++q) acc += (double)scratch[q * R + threadIdx.x];
         if (split) {
           const float af = (float)acc;
           for (int r = 0; r < CS; ++r) cluster.map_shared_rank(gather, r)[(size_t)CS * 2 * C + rank * R + threadIdx.x] = af;
         } else {
-          v_dz1[threadIdx.x] = hidden_g[(size_t)b * R + threadIdx.x] > 0.f ? (float)acc : 0.f;
+          v_dz1[threadIdx.x] = pre_hid > 0.f ? (float)acc : 0.f;
         }
       }
       if (split) {
@@ -470,18 +581,26 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
         if ((int)threadIdx.x < R) {
           double acc = 0.0;
           for (int r = 0; r < CS; ++r) acc += (double)gather[(size_t)CS * 2 * C + r * R + threadIdx.x];
-          v_dz1[threadIdx.x] = hidden_g[(size_t)b * R + threadIdx.x] > 0.f ? (float)acc : 0.f;
+          v_dz1[threadIdx.x] = pre_hid > 0.f ? (float)acc : 0.f;
         }
       }
       __syncthreads();
     }
+    GC_TS(22);
     {
       const int cpr = split ? (C + CS - 1) / CS : C;
       const int c_lo = split ? rank * cpr : 0, c_hi = split ? min(C, (rank + 1) * cpr) : C;
       for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
-        float dp = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < R; ++j) dp = fmaf(v_dz1[j], w1[(size_t)j * C + c], dp);
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};   // sixteen loads in flight, four chains
+        const float* wc = w1 + c;
+        int j = 0;
+#pragma unroll 4
+        for (; j + 3 < R; j += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d4[u] = fmaf(v_dz1[j + u], __ldg(wc + (size_t)(j + u) * C), d4[u]);
+        }
+        for (; j < R; ++j) d4[0] = fmaf(v_dz1[j], __ldg(wc + (size_t)j * C), d4[0]);
+        float dp = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         dp /= (float)P;
         if (split) {
           for (int r = 0; r < CS; ++r) cluster.map_shared_rank(v_dp, r)[c] = dp;
@@ -492,14 +611,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
       if (split) cluster.sync(); else __syncthreads();
     }
   }
+  GC_TS(23);
   // ---- 3. G1, G2 per channel, S1, S2 per sample (every CTA computes the same values in the same order)
   double s1 = 0.0, s2 = 0.0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float g1, g2;
     if (has_se) {
       const float sg = v_gate[c], dp = v_dp[c];
-      g1 = fmaf(dp, cpos_g[(size_t)b * C + c], sg * v_A1[c]);
-      g2 = fmaf(dp, spos_g[(size_t)b * C + c], sg * v_A2[c]);
+      const bool first = c == (int)threadIdx.x;
+      g1 = fmaf(dp, first ? pre_cpos : cpos_g[(size_t)b * C + c], sg * v_A1[c]);
+      g2 = fmaf(dp, first ? pre_spos : spos_g[(size_t)b * C + c], sg * v_A2[c]);
     } else {
       g1 = v_A1[c];
       g2 = v_A2[c];
@@ -514,10 +635,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
   }
   if (rank == 0 && has_se)
     for (int j = threadIdx.x; j < R; j += blockDim.x) dz1o[(size_t)b * R + j] = v_dz1[j];
-  s1 = block_sum(s1, red);
-  s2 = block_sum(s2, red);
+  gc_block_sum2(s1, s2, red);
   const float invM = 1.0f / ((float)P * (float)C);
   const float S1 = (float)s1 * invM, S2 = (float)s2 * invM;
+  GC_TS(24);
   // ---- 4. dy
   // dy = rstd * (gg * gamma - S1 - xhat * S2),  gg = mask ? dout * gate + dpool : 0
   //    = (mask ? dout * c1 + c2 : 0) + (y - mean) * k2 + k1      with the per-channel / per-sample constants below
@@ -542,6 +663,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1)
     }
     d.store(dstp + (size_t)p * C + col * V);
   }
+  GC_TS(25);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -673,3 +795,9 @@ template int gn_cluster_bwd<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bflo
                                            float*, cudaStream_t, bool*);
 
 }  // namespace bvae
+
+#ifdef BVAE_GC_TIMING
+extern "C" int bvae_gc_timestamps(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, bvae::g_gc_ts, sizeof(long long) * 32);
+}
+#endif

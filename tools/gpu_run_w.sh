@@ -1,2 +1,7 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_augment.py tests/test_gpu_train.py -x -q > gpurun_out/pytest_aug.log 2>&1; echo "pytest-aug rc=$?"; tail -30 gpurun_out/pytest_aug.log
+timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/pytest_all.log 2>&1; echo "pytest-all rc=$?"; tail -5 gpurun_out/pytest_all.log
+timeout 900 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2y.json 2> gpurun_out/bench_r2y.err; echo "bench rc=$?"
+python -c "
+import json
+d=json.load(open('gpurun_out/bench_r2y.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"
