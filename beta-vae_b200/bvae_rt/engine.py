@@ -138,6 +138,10 @@ class TrainEngine:
             self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(n)))
         self.arena = arena
         ops.set_grad_arena(arena)
+        # the GroupNorm / SE parameter gradients are reduced in one launch at the END of backward (ops.flush_gn_param_jobs)
+        # -- unless gradient buckets leave from hooks during backward, which would ship them unreduced
+        early = self.world > 1 and (self.dp_mode == "buckets" or (self._nvls is not None and self._nvls["overlap"]))
+        ops.set_gn_param_deferral(not early)
         if hasattr(model, "invalidate_packs"):
             model.invalidate_packs()
         self.last_grad_norm = None
@@ -387,6 +391,7 @@ class TrainEngine:
         for h in self._hooks:
             h.remove()
         ops.set_grad_arena(None)
+        ops.set_gn_param_deferral(True)
 
 
 class StagedBatch:

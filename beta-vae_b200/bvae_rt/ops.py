@@ -311,8 +311,32 @@ def gn_relu_se_fwd(y, gamma, beta, w1, b1, w2, b2, up=False, stat_part=None):
     return out, (stats, cpos, spos, hidden, gate)
 
 
-def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved, up=False):
-    """``up``: ``dout`` is the gradient w.r.t. the upsampled activation, [B,2H,2W,C]."""
+# Parameter-gradient reductions of the GroupNorm / SE blocks, deferred to the end of the backward pass: per block they
+# are a ~5 us kernel that nothing but the optimizer waits for, but launched where they arise they sit on the critical
+# path eight times.  ConvGnSeBlock.backward queues one job per block; an autograd final callback (runs when the whole
+# backward has been enqueued, inside a CUDA-graph capture too) launches them together.  The queued entries hold the
+# workspaces alive until then.  The engine switches this off when it exchanges gradient buckets from hooks DURING
+# backward (the reduction would then run after its bucket had left).
+_GN_DEFER = {"enabled": True, "jobs": [], "keep": []}
+
+
+def set_gn_param_deferral(enabled: bool):
+    _GN_DEFER["enabled"] = bool(enabled)
+
+
+def flush_gn_param_jobs():
+    jobs, _GN_DEFER["jobs"] = _GN_DEFER["jobs"], []
+    keep, _GN_DEFER["keep"] = _GN_DEFER["keep"], []
+    if jobs:
+        blob = b"".join(jobs)
+        with profiler.region("gn_bwd_params_batched"):
+            call("bvae_gn_bwd_params_batched", blob, len(jobs), _stream())
+    del keep
+
+
+def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved, up=False, defer=False):
+    """``up``: ``dout`` is the gradient w.r.t. the upsampled activation, [B,2H,2W,C].  ``defer`` (only inside an autograd
+    backward): the parameter gradients are filled by one batched launch when the backward pass ends."""
     B, H, W, Cc = y.shape
     P = H * W
     dev = y.device
@@ -325,17 +349,38 @@ def gn_relu_se_bwd(dout, y, gamma, beta, w1, b1, w2, b2, saved, up=False):
     if up:
         assert tuple(dout.shape) == (B, 2 * H, 2 * W, Cc), (dout.shape, y.shape)
         ws = _ws(query("bvae_gn_relu_se_up_workspace", B, H, W, Cc), dev)
-        with profiler.region(f"gn_relu_se_up_bwd[{H}x{W}x{Cc}]", nbytes=(dout.numel() + 2.0 * y.numel()) * y.element_size()):
+        name, nbytes = f"gn_relu_se_up_bwd[{H}x{W}x{Cc}]", (dout.numel() + 2.0 * y.numel()) * y.element_size()
+    else:
+        ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
+        # algorithmic bytes: read dout + read y + write dy
+        name, nbytes = f"gn_relu_se_bwd[{H}x{W}x{Cc}]", 3.0 * y.numel() * y.element_size()
+    # deferral needs autograd to ADOPT the returned gradient tensors (it then sees the late writes): true when it assigns
+    # (.grad is None) outside double-backward mode; when it would accumulate or clone, reduce now
+    if (defer and _GN_DEFER["enabled"] and not torch.is_grad_enabled()
+            and all(t is None or t.grad is None for t in (gamma, beta, w1, b1, w2, b2))):
+        import ctypes
+        job = ctypes.create_string_buffer(query("bvae_gn_params_job_bytes"))
+        with profiler.region(name, nbytes=nbytes):
+            call("bvae_gn_relu_se_bwd_deferred", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(w2), B, H, W, Cc,
+                 R, 1 if up else 0, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1),
+                 _p(db1), _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), job, _stream())
+        first = not _GN_DEFER["jobs"]
+        _GN_DEFER["jobs"].append(job.raw)
+        # (not the gradient tensors: a second reference makes AccumulateGrad clone them -- still unfilled -- instead of
+        #  adopting them; autograd / param.grad keep them alive)
+        _GN_DEFER["keep"].append((ws, gamma, beta, stats, cpos, spos, hidden))
+        if first:
+            torch.autograd.Variable._execution_engine.queue_callback(flush_gn_param_jobs)
+        return dy, dgamma, dbeta, dw1, db1, dw2, db2
+    with profiler.region(name, nbytes=nbytes):
+        if up:
             call("bvae_gn_relu_se_up_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B,
                  H, W, Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1),
                  _p(db1), _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
-        return dy, dgamma, dbeta, dw1, db1, dw2, db2
-    ws = _ws(query("bvae_gn_relu_se_workspace", B, P, Cc), dev)
-    # algorithmic bytes: read dout + read y + write dy
-    with profiler.region(f"gn_relu_se_bwd[{H}x{W}x{Cc}]", nbytes=3.0 * y.numel() * y.element_size()):
-        call("bvae_gn_relu_se_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B,
-             P, Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1), _p(db1),
-             _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
+        else:
+            call("bvae_gn_relu_se_bwd", _p(dout), _p(y), _p(dy), _p(gamma), _p(beta), _p(w1), _p(b1), _p(w2), _p(b2), B,
+                 P, Cc, R, _p(stats), _p(cpos), _p(spos), _p(hidden), _p(gate), _p(dgamma), _p(dbeta), _p(dw1), _p(db1),
+                 _p(dw2), _p(db2), _p(ws), ws.numel(), code_of(y), _stream())
     return dy, dgamma, dbeta, dw1, db1, dw2, db2
 
 
@@ -407,7 +452,7 @@ class ConvGnSeBlock(torch.autograd.Function):
         if ctx.up_after and not ctx.fuse_up:
             dout = upsample2x_bwd(dout)
         dy, dgw, dgb, dw1, db1, dw2, db2 = gn_relu_se_bwd(dout, y, gw, gb, w1, b1, w2, b2,
-                                                          (stats, cpos, spos, hidden, gate), up=ctx.fuse_up)
+                                                          (stats, cpos, spos, hidden, gate), up=ctx.fuse_up, defer=True)
         if ctx.first_tc:
             if ctx.needs_input_grad[0]:
                 raise lib.BvaeError("the tcgen05 first-layer path does not produce an input gradient")

@@ -578,20 +578,21 @@ __global__ void __launch_bounds__(kExThreads)
 // ------------------------------------------------------------------ backward: parameter gradients (sum over batch)
 // One WARP per job (lanes over the batch): the form for small job counts (a thread-per-job loop over B was latency
 // bound); job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R].
-__global__ void __launch_bounds__(256)
-    gn_bwd_params_warp_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
-                         const float* __restrict__ dz1, const float* __restrict__ cpos,
-                         const float* __restrict__ spos, const float* __restrict__ hidden,
-                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
-                         float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
-                         float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int has_se) {
+// (`block` of `nblocks`: the CTA's place inside this layer's share of the grid -- the whole grid for a stand-alone
+//  launch, a slice of it in gn_bwd_params_batched_kernel)
+__device__ __forceinline__ void gn_bwd_params_warp_body(
+    const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
+    const float* __restrict__ dz1, const float* __restrict__ cpos, const float* __restrict__ spos,
+    const float* __restrict__ hidden, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
+    float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int has_se, int block, int nblocks) {
   // job space: [0, C) gamma/beta(+db2); then dw2 [C*R]; then dw1 [R*C]; then db1 [R].
   // One WARP per job, lanes stride over the batch (the per-thread serial loop over B was latency bound).
   const long long n_gb = C, n_w2 = has_se ? (long long)C * R : 0, n_w1 = n_w2, n_b1 = has_se ? R : 0;
   const long long total = n_gb + n_w2 + n_w1 + n_b1;
   const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp0 = ((long long)block * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)nblocks * blockDim.x) >> 5;
   for (long long i = warp0; i < total; i += nwarps) {
     if (i < n_gb) {
       const int c = (int)i;
@@ -642,21 +643,20 @@ __global__ void __launch_bounds__(256)
 // (C = 512, R = 64: 66 k jobs took 22.7 us thread-per-job, 29 us warp-per-job).  CTA = 32 channels x 8 hidden units
 // (grid C/32 x R/8: enough CTAs that each one is a single round of loads, 32 FMAs per thread and a store); lane =
 // channel, warp = hidden unit; batch in chunks of 32 through shared memory.  Fixed summation order (b ascending).
-__global__ void __launch_bounds__(256)
-    gn_bwd_params_tiled_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
-                               const float* __restrict__ dz1, const float* __restrict__ cpos,
-                               const float* __restrict__ spos, const float* __restrict__ hidden,
-                               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
-                               float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
-                               float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R) {
+__device__ __forceinline__ void gn_bwd_params_tiled_body(
+    const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
+    const float* __restrict__ dz1, const float* __restrict__ cpos, const float* __restrict__ spos,
+    const float* __restrict__ hidden, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
+    float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R, int bx, int by) {
   __shared__ float dz2s[32][33], pools[32][33];
   __shared__ float hids[32][9], dz1s[32][9];
-  const int c0 = blockIdx.x * 32, j0 = blockIdx.y * 8;
+  const int c0 = bx * 32, j0 = by * 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = c0 + lane, j = j0 + warp;
   const bool cok = c < C, jok = j < R;
   const float gc = cok ? gamma[c] : 0.f, bc = cok ? beta[c] : 0.f, invP = 1.f / (float)P;
-  const bool sums = blockIdx.y == 0;          // these CTAs also produce dgamma / dbeta / db2 for their channels
+  const bool sums = by == 0;                  // these CTAs also produce dgamma / dbeta / db2 for their channels
   float acc2 = 0.f, acc1 = 0.f, dg = 0.f, db = 0.f, d2 = 0.f;
   for (int b0 = 0; b0 < B; b0 += 32) {
     const int nb = min(32, B - b0);
@@ -720,13 +720,67 @@ __global__ void __launch_bounds__(256)
     for (int w = 0; w < 8; ++w) a += red[(warp * 8 + w) * 32 + lane];
     (warp == 0 ? dgamma : (warp == 1 ? dbeta : db2))[c] = a;
   }
-  if (blockIdx.x == 0 && warp == 0) {             // db1 for this CTA's hidden units: lanes over the batch
+  if (bx == 0 && warp == 0) {                     // db1 for this CTA's hidden units: lanes over the batch
     for (int jj = 0; jj < 8 && j0 + jj < R; ++jj) {
       float a = 0.f;
       for (int b = lane; b < B; b += 32) a += dz1[(size_t)b * R + j0 + jj];
       a = warp_sum(a);
       if (lane == 0) db1[j0 + jj] = a;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    gn_bwd_params_warp_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
+                              const float* __restrict__ dz1, const float* __restrict__ cpos, const float* __restrict__ spos,
+                              const float* __restrict__ hidden, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                              float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                              float* __restrict__ db2, int B, int P, int C, int R, int has_se) {
+  gn_bwd_params_warp_body(G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2, B, P, C, R,
+                          has_se, (int)blockIdx.x, (int)gridDim.x);
+}
+__global__ void __launch_bounds__(256)
+    gn_bwd_params_tiled_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ dz2,
+                               const float* __restrict__ dz1, const float* __restrict__ cpos,
+                               const float* __restrict__ spos, const float* __restrict__ hidden,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
+                               float* __restrict__ dbeta, float* __restrict__ dw1, float* __restrict__ db1,
+                               float* __restrict__ dw2, float* __restrict__ db2, int B, int P, int C, int R) {
+  gn_bwd_params_tiled_body(G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2, B, P, C, R,
+                           (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// The parameter gradients of SEVERAL blocks in one launch.  Each block's reduction over the batch is a few
+// microseconds of work behind a launch, and nothing downstream of it runs before the optimizer: issued per block they
+// are eight serialised small kernels on the backward's critical path (~35 us of a 1.4 ms step).  The caller collects one
+// job per block (bvae_gn_relu_se_bwd_deferred) and flushes them together when backward has been enqueued.
+struct GnParamJob {
+  const float *G1, *G2, *dz2, *dz1, *cpos, *spos, *hidden, *gamma, *beta;
+  float *dgamma, *dbeta, *dw1, *db1, *dw2, *db2;
+  int B, P, C, R, has_se;
+  int tiled;       // 1: tiled kernel body, grid (C/32) x (R/8); 0: warp-per-job body over `blocks` CTAs
+  int blocks;
+  int pad_;
+};
+static constexpr int kGnMaxJobs = 16;
+struct GnParamBatch {
+  GnParamJob job[kGnMaxJobs];
+  int first[kGnMaxJobs + 1];   // first CTA of job i; first[n] = grid size
+  int n;
+};
+__global__ void __launch_bounds__(256) gn_bwd_params_batched_kernel(const __grid_constant__ GnParamBatch bt) {
+  int l = 0;
+  while (l + 1 < bt.n && (int)blockIdx.x >= bt.first[l + 1]) ++l;
+  const GnParamJob& j = bt.job[l];
+  const int lb = (int)blockIdx.x - bt.first[l];
+  if (j.tiled) {
+    const int gx = (j.C + 31) / 32;
+    gn_bwd_params_tiled_body(j.G1, j.G2, j.dz2, j.dz1, j.cpos, j.spos, j.hidden, j.gamma, j.beta, j.dgamma, j.dbeta, j.dw1,
+                             j.db1, j.dw2, j.db2, j.B, j.P, j.C, j.R, lb % gx, lb / gx);
+  } else {
+    gn_bwd_params_warp_body(j.G1, j.G2, j.dz2, j.dz1, j.cpos, j.spos, j.hidden, j.gamma, j.beta, j.dgamma, j.dbeta, j.dw1,
+                            j.db1, j.dw2, j.db2, j.B, j.P, j.C, j.R, j.has_se, lb, j.blocks);
   }
 }
 
@@ -924,19 +978,31 @@ __global__ void __launch_bounds__(kGnThreads)
   }
 }
 
+// `job` non-null: describe the launch instead of issuing it (deferred, see gn_bwd_params_batched_kernel)
 static int launch_gn_params(const float* G1, const float* G2, const float* dz2, const float* dz1, const float* cpos,
                             const float* spos, const float* hidden, const float* gamma, const float* beta,
                             float* dgamma, float* dbeta, float* dw1, float* db1, float* dw2, float* db2, int B, int P,
-                            int C, int R, bool has_se, cudaStream_t st) {
+                            int C, int R, bool has_se, cudaStream_t st, GnParamJob* job = nullptr) {
   const long long jobs = (long long)C + (has_se ? 2LL * C * R + R : 0);
-  if (has_se && jobs > 4096) {
+  const bool tiled = has_se && jobs > 4096;
+  int blocks;
+  if (tiled) {
+    blocks = ((C + 31) / 32) * ((R + 7) / 8);
+  } else {
+    blocks = (int)((jobs + 7) / 8);  // one warp per job, 8 warps per CTA
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  }
+  if (job) {
+    *job = GnParamJob{G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2,
+                      B, P, C, R, has_se ? 1 : 0, tiled ? 1 : 0, blocks, 0};
+    return BVAE_OK;
+  }
+  if (tiled) {
     gn_bwd_params_tiled_kernel<<<dim3((C + 31) / 32, (R + 7) / 8), 256, 0, st>>>(G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma,
                                                               dbeta, dw1, db1, dw2, db2, B, P, C, R);
     BVAE_LAUNCH_CHECK("gn_bwd_params_tiled");
     return BVAE_OK;
   }
-  int blocks = (int)((jobs + 7) / 8);  // one warp per job, 8 warps per CTA
-  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   gn_bwd_params_warp_kernel<<<blocks, 256, 0, st>>>(G1, G2, dz2, dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1,
                                                     db1, dw2, db2, B, P, C, R, has_se ? 1 : 0);
   BVAE_LAUNCH_CHECK("gn_bwd_params");
@@ -1053,7 +1119,7 @@ template <typename T>
 static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, const float* beta, const float* w1,
                        const float* w2, int B, int H, int W, int C, int R, int up, const float* stats, const float* cpos,
                        const float* spos, const float* hidden, const float* gate, float* dgamma, float* dbeta,
-                       float* dw1, float* db1, float* dw2, float* db2, void* ws, cudaStream_t st) {
+                       float* dw1, float* db1, float* dw2, float* db2, void* ws, cudaStream_t st, GnParamJob* job) {
   const int P = H * W;
   GnGeom g;
   BVAE_REQUIRE(gn_geom(B, P, C, Vec16<T>::N, &g), BVAE_ERR_UNSUPPORTED,
@@ -1067,7 +1133,7 @@ static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, con
     if (rc != BVAE_OK) return rc;
     if (handled)
       return launch_gn_params(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2,
-                              B, P, C, R, has_se, st);
+                              B, P, C, R, has_se, st, job);
   }
   dim3 grid(g.nchunks, B);
   const size_t sm = (size_t)2 * g.rows * C * sizeof(float);
@@ -1092,7 +1158,7 @@ static int gn_bwd_impl(const T* dout, const T* y, T* dy, const float* gamma, con
   BVAE_LAUNCH_CHECK("gn_bwd_apply");
   // parameter gradients last: they are off the critical path of the data gradient
   return launch_gn_params(w.G1, w.G2, w.dz2, w.dz1, cpos, spos, hidden, gamma, beta, dgamma, dbeta, dw1, db1, dw2, db2, B,
-                          P, C, R, has_se, st);
+                          P, C, R, has_se, st, job);
 }
 
 }  // namespace bvae
@@ -1137,7 +1203,7 @@ static int gn_bwd_entry(const void* dout, const void* y, void* dy, const float* 
                         const float* w2, int B, int H, int W, int C, int R, int up, const float* stats, const float* cpos,
                         const float* spos, const float* hidden, const float* gate, float* dgamma, float* dbeta,
                         float* dw1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
-                        bvae_stream_t stream) {
+                        bvae_stream_t stream, GnParamJob* job = nullptr) {
   BVAE_REQUIRE(dout && y && dy && gamma && beta && stats && dgamma && dbeta && ws, BVAE_ERR_ARG,
                "gn_relu_se_bwd: null pointer");
   BVAE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, BVAE_ERR_ARG, "gn_relu_se_bwd: empty shape");
@@ -1151,11 +1217,11 @@ static int gn_bwd_entry(const void* dout, const void* y, void* dy, const float* 
   cudaStream_t st = as_stream(stream);
   if (dtype == BVAE_F32)
     return gn_bwd_impl<float>((const float*)dout, (const float*)y, (float*)dy, gamma, beta, w1, w2, B, H, W, C, R, up,
-                              stats, cpos, spos, hidden, gate, dgamma, dbeta, dw1, db1, dw2, db2, ws, st);
+                              stats, cpos, spos, hidden, gate, dgamma, dbeta, dw1, db1, dw2, db2, ws, st, job);
   if (dtype == BVAE_BF16)
     return gn_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, gamma,
                                       beta, w1, w2, B, H, W, C, R, up, stats, cpos, spos, hidden, gate, dgamma, dbeta,
-                                      dw1, db1, dw2, db2, ws, st);
+                                      dw1, db1, dw2, db2, ws, st, job);
   BVAE_REQUIRE(false, BVAE_ERR_UNSUPPORTED, "gn_relu_se_bwd: dtype %d", dtype);
 }
 
@@ -1199,6 +1265,47 @@ extern "C" int bvae_gn_relu_se_up_bwd(const void* d_up, const void* y, void* dy,
   (void)b2;
   return gn_bwd_entry(d_up, y, dy, gamma, beta, w1, w2, B, H, W, C, R, 1, stats, cpos, spos, hidden, gate, dgamma, dbeta,
                       dw1, db1, dw2, db2, ws, ws_bytes, dtype, stream);
+}
+
+extern "C" size_t bvae_gn_params_job_bytes(void) { return sizeof(GnParamJob); }
+
+/* bvae_gn_relu_se_bwd / _up_bwd (up != 0: dout is [B][2H][2W][C]) WITHOUT the reduction of the parameter gradients over
+ * the batch: dy is produced, the per-sample terms stay in `ws`, and `job_out` (HOST memory, bvae_gn_params_job_bytes())
+ * receives the description of the missing launch.  `ws` and every pointer passed here must stay valid until the job has
+ * gone through bvae_gn_bwd_params_batched on the same stream. */
+extern "C" int bvae_gn_relu_se_bwd_deferred(const void* dout, const void* y, void* dy, const float* gamma, const float* beta,
+                                            const float* w1, const float* w2, int B, int H, int W, int C, int R, int up,
+                                            const float* stats, const float* cpos, const float* spos,
+                                            const float* hidden, const float* gate, float* dgamma, float* dbeta,
+                                            float* dw1, float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes,
+                                            int dtype, void* job_out, bvae_stream_t stream) {
+  BVAE_REQUIRE(job_out, BVAE_ERR_ARG, "gn_relu_se_bwd_deferred: null job_out");
+  return gn_bwd_entry(dout, y, dy, gamma, beta, w1, w2, B, H, W, C, R, up ? 1 : 0, stats, cpos, spos, hidden, gate, dgamma,
+                      dbeta, dw1, db1, dw2, db2, ws, ws_bytes, dtype, stream, reinterpret_cast<GnParamJob*>(job_out));
+}
+
+/* One launch for the parameter gradients of `njobs` deferred blocks (`jobs`: HOST array of job records, back to back). */
+extern "C" int bvae_gn_bwd_params_batched(const void* jobs, int njobs, bvae_stream_t stream) {
+  BVAE_REQUIRE(jobs && njobs > 0, BVAE_ERR_ARG, "gn_bwd_params_batched: no jobs");
+  const GnParamJob* src = reinterpret_cast<const GnParamJob*>(jobs);
+  cudaStream_t st = as_stream(stream);
+  for (int i0 = 0; i0 < njobs; i0 += kGnMaxJobs) {
+    GnParamBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    bt.n = njobs - i0 < kGnMaxJobs ? njobs - i0 : kGnMaxJobs;
+    int total = 0;
+    for (int i = 0; i < bt.n; ++i) {
+      bt.job[i] = src[i0 + i];
+      BVAE_REQUIRE(bt.job[i].blocks > 0 && bt.job[i].G1 && bt.job[i].dgamma, BVAE_ERR_ARG, "gn_bwd_params_batched: bad job %d",
+                   i0 + i);
+      bt.first[i] = total;
+      total += bt.job[i].blocks;
+    }
+    bt.first[bt.n] = total;
+    gn_bwd_params_batched_kernel<<<total, 256, 0, st>>>(bt);
+    BVAE_LAUNCH_CHECK("gn_bwd_params_batched");
+  }
+  return BVAE_OK;
 }
 
 /* 1 when bvae_gn_relu_se_fwd would run the single-launch cluster-resident kernel for this shape (the caller then keeps

@@ -136,6 +136,18 @@ int bvae_gn_relu_se_bwd(const void* dout, const void* y, void* dy, const float* 
                         const float* hidden, const float* gate, float* dgamma, float* dbeta, float* dw1,
                         float* db1, float* dw2, float* db2, void* ws, size_t ws_bytes, int dtype,
                         bvae_stream_t stream);
+/* Deferred form of the two backward entry points (up != 0: the fused-upsample one, dout = [B][2H][2W][C]): dy is
+ * produced now; the reduction of the parameter gradients over the batch -- a few microseconds of work behind a launch,
+ * needed only by the optimizer -- is described in `job_out` (HOST memory, bvae_gn_params_job_bytes()) instead of being
+ * launched.  bvae_gn_bwd_params_batched then runs the jobs of all blocks in ONE launch (`jobs`: host array of records,
+ * back to back) once backward has been enqueued.  `ws` and every pointer of a job must stay valid until then. */
+size_t bvae_gn_params_job_bytes(void);
+int bvae_gn_relu_se_bwd_deferred(const void* dout, const void* y, void* dy, const float* gamma, const float* beta,
+                                 const float* w1, const float* w2, int B, int H, int W, int C, int R, int up,
+                                 const float* stats, const float* cpos, const float* spos, const float* hidden,
+                                 const float* gate, float* dgamma, float* dbeta, float* dw1, float* db1, float* dw2,
+                                 float* db2, void* ws, size_t ws_bytes, int dtype, void* job_out, bvae_stream_t stream);
+int bvae_gn_bwd_params_batched(const void* jobs, int njobs, bvae_stream_t stream);
 /* The same block followed by the NEXT decoder block's nn.Upsample(x2, bilinear, align_corners=False)
  * (beta_vae.py:52-53), fused: the activation is never written at its own resolution.
  *   fwd: y [B][H][W][C] -> out_up [B][2H][2W][C] = upsample2x(relu(gn(y)) * gate)

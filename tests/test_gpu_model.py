@@ -147,6 +147,38 @@ def test_streaming_groupnorm_path_matches_cluster_path(prec, monkeypatch):
     assert whole <= tol * (50 if prec == "fp32" else 1), whole       # fp32: ill-conditioned tensors, summation order
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_deferred_groupnorm_parameter_gradients_are_bit_identical(prec):
+    """The GroupNorm / SE parameter gradients of all blocks are reduced over the batch by ONE launch when backward ends
+    (ops.flush_gn_param_jobs, an autograd final callback) instead of one small launch per block: same kernels' bodies,
+    same summation order -> every gradient must be bit-equal to the per-block form, and nothing may be left queued."""
+    import cfgs
+    from bvae_rt import lib, ops
+    cfg = cfgs.shipped("beta_vae_se")
+    cfg["model"]["base_channels"] = 16
+    torch.manual_seed(0)
+    m = build_model(cfg, None, prec).apply(cfgs.weight_init)
+    x, eps = torch.rand(4, 1, 128, 128), torch.randn(4, cfg["model"]["latent_dim"])
+    kw = dict(beta=1.0, capacity=30.0, free_bits=0.0, capacity_weight=1.0)
+    lib.load()
+    run_loss(m, x, eps, kw)                                        # builds the cached weight packs (their own launches)
+    n0 = lib.query("bvae_launch_count")
+    out_a, g_a = run_loss(m, x, eps, kw)
+    n_deferred = lib.query("bvae_launch_count") - n0
+    assert ops._GN_DEFER["jobs"] == [] and ops._GN_DEFER["keep"] == []
+    ops.set_gn_param_deferral(False)
+    try:
+        n0 = lib.query("bvae_launch_count")
+        out_b, g_b = run_loss(m, x, eps, kw)
+        n_direct = lib.query("bvae_launch_count") - n0
+    finally:
+        ops.set_gn_param_deferral(True)
+    assert float(out_a["total"]) == float(out_b["total"])
+    for k in g_a:
+        assert torch.equal(g_a[k], g_b[k]), k
+    assert n_deferred == n_direct - 7                              # eight per-block launches became one
+
+
 def test_encode_decode_forward_api():
     import cfgs
     cfg = cfgs.small()
