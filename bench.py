@@ -317,11 +317,12 @@ class ClockSampler:
 # under profiles/ (r1_ncu_conv_halo.txt, r1_ncu_wgrad_halo.txt, r1_ncu_gn_cluster.txt, r1_ncu_s2dgrad_finalconv.txt,
 # refreshed by the r2_* files when a kernel changed)
 NCU_TRAFFIC = {
-    "conv_fprop_dec3": 84.93e6,
-    "conv_wgrad_dec3": 135.6e6,
-    "gn_fwd_64x64x64": 16.8e6 + 0.0,      # read = the tensor once; the write is still in L2 when the kernel ends
-    "gn_fwd_128x128x64": None,
-    "finalconv_fwd": 70.5e6,
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r2_ncu_step_kernels.txt (B = 32, in-step launches)
+    "conv_fprop_dec3": 67.22e6 + 21.88e6,   # most of the 67 MB output is still in L2 when the kernel ends
+    "conv_wgrad_dec3": 135.6e6 + 4.77e6,    # + 24.1 MB read by the split-K reduce (conv_wgrad_halo_reduce_kernel)
+    "gn_fwd_64x64x64": 16.84e6 + 0.0,       # read = the tensor once; the write is still in L2 when the kernel ends
+    "gn_fwd_128x128x64": (67.40e6 + 0.51e6) + (67.13e6 + 24.61e6),   # gn_pool_kernel + gn_scale_kernel (statistics: conv epilogue)
+    "finalconv_fwd": 69.24e6 + 1.91e6,
 }
 
 
@@ -699,21 +700,32 @@ def cuda_main(args):
     more = [fprop_entry]
 
     # (b2) HBM-bound kernels named by north_star: GroupNorm+ReLU+SE and the loss kernel
-    def gn_case(Hs, C, nbuf, key):
+    def gn_case(Hs, C, nbuf, key, conv_stats=False):
+        """``conv_stats``: the tensor comes out of the 3x3 convolution with its GroupNorm statistic partials, as in the
+        step (the 2 MB samples of dec3 take the streaming passes, whose statistics ride in the conv epilogue)."""
         R = max(1, C // cfg["model"]["se_reduction_ratio"])
-        ys = [torch.randn(batch, Hs, Hs, C, device=dev).to(bf) for _ in range(nbuf)]
         gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
         w1, b1 = torch.randn(R, C, device=dev) * 0.1, torch.zeros(R, device=dev)
         w2, b2 = torch.randn(C, R, device=dev) * 0.1, torch.zeros(C, device=dev)
-        us = device_us(lambda i: ops.gn_relu_se_fwd(ys[i % nbuf], gam, bet, w1, b1, w2, b2), 2 * nbuf)
+        if conv_stats:
+            wc = torch.randn(C, C, 3, 3, device=dev) * 0.05
+            wp = ops.pack_conv(wc, BF16, False, ops.conv_weight_layout(Hs, Hs, C, C, 1, BF16, 0))
+            pairs = [ops.conv3x3_fprop(torch.randn(batch, Hs, Hs, C, device=dev).to(bf), wp, torch.zeros(C, device=dev), C, 1,
+                                       BF16, want_stats=True) for _ in range(nbuf)]
+            ys, sps = [p[0] for p in pairs], [p[1] for p in pairs]
+        else:
+            ys = [torch.randn(batch, Hs, Hs, C, device=dev).to(bf) for _ in range(nbuf)]
+            sps = [None] * nbuf
+        us = device_us(lambda i: ops.gn_relu_se_fwd(ys[i % nbuf], gam, bet, w1, b1, w2, b2, stat_part=sps[i % nbuf]), 2 * nbuf)
         nbytes = 2.0 * ys[0].numel() * 2
-        more.append({"kernel": f"gn_relu_se_fwd {Hs}x{Hs}x{C}", "bound": "hbm", "achieved": nbytes / us / 1e3,
+        more.append({"kernel": f"gn_relu_se_fwd {Hs}x{Hs}x{C}" + (" (statistics from the conv epilogue)" if sps[0] is not None else ""),
+                     "bound": "hbm", "achieved": nbytes / us / 1e3,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / us / 1e3 / peaks["hbm_gbs"],
                      "traffic": NCU_TRAFFIC.get(key) if batch == 32 else None, "algorithmic_bytes": nbytes,
                      "us_per_launch": us})
 
     gn_case(size // 2, Cc, 8, "gn_fwd_64x64x64")
-    gn_case(size, Cc, 3, "gn_fwd_128x128x64")
+    gn_case(size, Cc, 3, "gn_fwd_128x128x64", conv_stats=True)
     hs_f = [torch.randn(batch, size, size, Cc, device=dev).to(bf) for _ in range(3)]
     w_f = torch.randn(1, Cc, 3, 3, device=dev) * 0.05
     b_f = torch.zeros(1, device=dev)
