@@ -531,7 +531,8 @@ def cuda_main(args):
         dp_check = {"param_sum_min": float(lo[0]), "param_sum_max": float(hi[0]),
                     "param_bits_min": float(lo[1]), "param_bits_max": float(hi[1]),
                     "identical": bool(torch.equal(lo, hi)), "after_steps": warm,
-                    "exchange": engine.dp_mode, "exchange_sums_exactly": bool(ex[0] > 0.5),
+                    "exchange": engine.dp_mode + (f"/{engine._nvls['algo']}" if engine._nvls is not None else ""),
+                    "exchange_sums_exactly": bool(ex[0] > 0.5),
                     "exchange_timeouts": engine.nvls_status(), "exchange_us_isolated": exchange_us,
                     "exchange_bytes": engine.numel * 4,
                     "what": "sum and int32-bit-pattern sum of every rank's flat fp32 parameter buffer, all-reduce MIN vs MAX"}

@@ -147,7 +147,11 @@ class TrainEngine:
         self.last_grad_norm = None
 
     # ------------------------------------------------------------------ NVLS exchange (symmetric gradient buffer)
-    NVLS_BLOCKS = int(__import__("os").environ.get("BVAE_NVLS_BLOCKS", "64"))   # same on every rank
+    # Exchange kernel and its grid, the same on every rank.  Measured (profiles/r2_scale_n{2,4,8}_{mc,p2p}*.json, 38.3 MB):
+    # peer loads / stores beat the multicast form at 2 ranks (89 vs 138 us) and 4 ranks (119 vs 133 us); at 8 ranks both
+    # take 137-139 us, and the in-switch reduction is kept there.  BVAE_NVLS_ALGO = mc | p2p and BVAE_NVLS_BLOCKS override.
+    NVLS_BLOCKS = 64
+    NVLS_ALGO = "auto"
 
     def _alloc_grad_buffer(self, n, dev):
         """The flat gradient buffer.  With world > 1 on CUDA it is allocated as symmetric memory and bound to the group's
@@ -174,6 +178,12 @@ class TrainEngine:
             hdl = symm.rendezvous(g, group=gname)
             if not hdl.multicast_ptr:
                 raise RuntimeError("the group has no NVLS multicast support")
+            algo = os.environ.get("BVAE_NVLS_ALGO", self.NVLS_ALGO)
+            if algo == "auto":
+                algo = "p2p" if self.world in (2, 4) else "mc"
+            if algo == "p2p" and self.world not in (2, 4, 8):
+                algo = "mc"
+            self.NVLS_BLOCKS = int(os.environ.get("BVAE_NVLS_BLOCKS", "128" if algo == "p2p" else "64"))
             nflags = query("bvae_allreduce_nvls_flag_count", self.NVLS_BLOCKS, self.world)
             flags = symm.empty(nflags, dtype=torch.int32, device=dev)
             flags.zero_()
@@ -181,7 +191,10 @@ class TrainEngine:
             state = torch.zeros(query("bvae_allreduce_nvls_state_bytes"), dtype=torch.uint8, device=dev)
             torch.cuda.synchronize(dev)
             dist.barrier(group=self.pg)                          # every rank's flags are zero before the first exchange
+            # algo "mc" = in-switch reduction through the multicast object (allreduce_nvls_kernel), "p2p" = the same exchange
+            # through plain peer mappings (allreduce_p2p_kernel); both on this symmetric buffer
             self._nvls = {"hdl": hdl, "fh": fh, "flags": flags, "state": state, "mc": int(hdl.multicast_ptr),
+                          "buf_ptrs": int(hdl.buffer_ptrs_dev), "algo": algo,
                           "flag_ptrs": int(fh.buffer_ptrs_dev), "n": n, "stream": torch.cuda.Stream(device=dev),
                           "overlap": os.environ.get("BVAE_NVLS_OVERLAP", "0") == "1", "launched": 0}
             self.dp_mode = "nvls"
@@ -198,8 +211,13 @@ class TrainEngine:
         """Sum floats [lo, hi) of the gradient buffer over the ranks, on the current stream."""
         nv = self._nvls
         hi = nv["n"] if hi is None else hi
-        call("bvae_allreduce_nvls", nv["mc"] + 4 * lo, hi - lo, nv["flag_ptrs"], nv["state"].data_ptr(),
-             dist.get_rank(self.pg), self.world, self.NVLS_BLOCKS, torch.cuda.current_stream().cuda_stream)
+        st = torch.cuda.current_stream().cuda_stream
+        if nv["algo"] == "p2p":
+            call("bvae_allreduce_p2p", nv["buf_ptrs"], lo, hi - lo, nv["flag_ptrs"], nv["state"].data_ptr(),
+                 dist.get_rank(self.pg), self.world, self.NVLS_BLOCKS, st)
+        else:
+            call("bvae_allreduce_nvls", nv["mc"] + 4 * lo, hi - lo, nv["flag_ptrs"], nv["state"].data_ptr(),
+                 dist.get_rank(self.pg), self.world, self.NVLS_BLOCKS, st)
 
     def _launch_reduce_nvls(self, bi):
         """Bucket ``bi`` is complete on the current stream: exchange it on the side stream (fork; finish_reduce joins)."""

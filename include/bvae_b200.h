@@ -292,6 +292,12 @@ size_t bvae_allreduce_nvls_state_bytes(void);
 size_t bvae_allreduce_nvls_flag_count(int nblocks, int world);
 int bvae_allreduce_nvls(void* mc_ptr, size_t n, void* flag_ptrs, void* state, int rank, int world, int nblocks,
                         bvae_stream_t stream);
+/* Same sum through plain peer mappings (NVLink loads / stores, no multicast): rank r loads the `world` copies of its
+ * slice through `buf_ptrs` (DEVICE array of `world` pointers to element 0 of every rank's buffer as mapped on this
+ * device), adds them in rank order and stores the sum into every copy.  Range = floats [off, off + n), multiples of 4;
+ * world in {2, 4, 8}.  Flags / state / nblocks as above. */
+int bvae_allreduce_p2p(void* buf_ptrs, size_t off, size_t n, void* flag_ptrs, void* state, int rank, int world,
+                       int nblocks, bvae_stream_t stream);
 
 /* Input pipeline: uint8 image bytes -> fp32 in [0, 1], dst[i] = float(src[i]) / 255 with IEEE division -- the values
  * torchvision's ToTensor produces from the dataset's PNGs (datautils.py:59-65), so shipping bytes over PCIe and
