@@ -32,18 +32,22 @@ struct GnGeom {
   int nchunks;
 };
 
-// Pixels per chunk (= per CTA).  The passes are pure streaming, so what matters is bytes in flight: enough CTAs to
-// fill every SM several times over (>= ~4 per SM when the tensor allows it) and at most 16 vectors per thread.  The
-// round-1 rule (a fixed 64 KB per CTA) left the small deep layers with 32 CTAs on 148 SMs.
+// Pixels per chunk (= per CTA).  The passes are pure streaming, so what matters is bytes in flight and whole waves:
+// four CTAs are resident per SM (64 registers x 256 threads), so the grid is sized to AT MOST 4 x SMs CTAs -- one wave --
+// as long as a thread then walks no more than 32 vectors; beyond that the tensor is large enough for several waves.
+// (Round 1: a fixed 64 KB per CTA left the small deep layers with 32 CTAs on 148 SMs.  Round 2 first capped a thread at
+// 16 vectors, which gave dec3's 67 MB tensors 1024 CTAs = 1.73 waves of short-lived CTAs.)
 static inline int gn_pixels_per_chunk(int B, int P, int C, int rows) {
   if (rows < 1) rows = 1;
+  static const int one_wave = getenv("BVAE_GN_WAVE") == nullptr || atoi(getenv("BVAE_GN_WAVE")) != 0;
   const long long want = 4LL * num_sms();                 // CTAs
-  long long nch = (want + B - 1) / (B > 0 ? B : 1);
+  long long nch = one_wave ? want / (B > 0 ? B : 1) : (want + B - 1) / (B > 0 ? B : 1);
   if (nch < 1) nch = 1;
   long long pc = (P + nch - 1) / nch;
   pc = (pc + rows - 1) / rows * rows;                      // whole rounds of the CTA's pixel rows
   if (pc < rows) pc = rows;
-  if (pc > 16LL * rows) pc = 16LL * rows;
+  const long long cap = (one_wave ? 32LL : 16LL) * rows;
+  if (pc > cap) pc = cap;
   const long long floor_pc = (32768 / (C > 0 ? C : 1)) / 64;   // never below ~1 KB per CTA
   if (pc < floor_pc) pc = floor_pc;
   if (pc > P) pc = P;

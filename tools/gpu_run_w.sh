@@ -1,7 +1,4 @@
 set -x
-timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/pytest_all.log 2>&1; echo "pytest-all rc=$?"; tail -5 gpurun_out/pytest_all.log
-timeout 900 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2z.json 2> gpurun_out/bench_r2z.err; echo "bench rc=$?"
-python -c "
-import json
-d=json.load(open('gpurun_out/bench_r2z.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"
+timeout 900 python -m pytest tests/test_gpu_ops.py -x -q -k "gn" > gpurun_out/pytest_gn.log 2>&1; echo "pytest-gn rc=$?"; tail -2 gpurun_out/pytest_gn.log
+for v in 1 0; do BVAE_GN_WAVE=$v timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | grep "^{" | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('wave=$v', d['ms_per_step'], [ (r['kernel'][:28], round(r['us_per_launch'],1)) for r in d['roofline_more']])"; done
