@@ -87,9 +87,21 @@ __global__ void __launch_bounds__(256) pack_conv_tiled_kernel(const PackJobs job
   for (int tile = blockIdx.x; tile < tiles_ci * tiles_co; tile += gridDim.x) {
     const int co0 = (tile / tiles_ci) * 32, ci0 = (tile % tiles_ci) * 32;
     const int nci = min(32, jb.Cin - ci0), nco = min(32, jb.Cout - co0);
+    // every CTA moves at most a tile or two, so a tile's latency is the kernel's: all nine loads of a source row are
+    // issued before the first store (the element loop above them ran 36 dependent load -> store rounds per warp, ~20 us)
     for (int r = warp; r < nco; r += 8) {
       const float* src = jb.w + ((size_t)(co0 + r) * jb.Cin + ci0) * 9;
-      for (int e = lane; e < nci * 9; e += 32) sm[r][e] = src[e];
+      float v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int e = lane + 32 * k;
+        v[k] = e < nci * 9 ? __ldg(src + e) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int e = lane + 32 * k;
+        if (e < nci * 9) sm[r][e] = v[k];
+      }
     }
     __syncthreads();
     if (co_major) {

@@ -31,7 +31,34 @@ def check(name, got, ref, rtol, gnorm=0.0, floor=0.0):
     return rel_err(got, ref)
 
 
-def check_vs_exact(name, got, ref_lp, exact, rtol, gnorm=0.0, floor=0.0, slack=4.0):
+def tensor_kind(name: str) -> str:
+    """'encoder.2.se.block.fc.0.weight' / 'decoder_blocks.0.se.block.fc.0.weight' -> 'se.block.fc.0.weight': the same
+    parameter of every encoder / decoder block."""
+    parts = name.split(".")
+    if parts[0] in ("encoder", "decoder_blocks") and len(parts) > 2 and parts[1].isdigit():
+        return ".".join(parts[2:])
+    return name
+
+
+def own_error_by_kind(names, ref_lp, exact):
+    """max over the tensors of a kind of the low-precision reference's own relative error vs ``exact``.
+
+    The reference's error on ONE small tensor is a single draw of rounding noise: on a 32-element SE bias under bf16 it
+    moves by 2x between two CPU hosts (thread count changes the reduction order of the autocast reference) and ours
+    moves as much when a kernel's summation order changes, so the ratio of the two is heavy-tailed.  The largest error
+    the reference makes on any block's tensor of the same kind is the steadier yardstick for "the noise this kind of
+    tensor carries at this precision"."""
+    out = {}
+    for k in names:
+        e = exact[k].detach().double().cpu()
+        n = float(e.norm())
+        r = float((ref_lp[k].detach().double().cpu() - e).norm()) / (n if n > 0 else 1.0)
+        kind = tensor_kind(k)
+        out[kind] = max(out.get(kind, 0.0), r)
+    return out
+
+
+def check_vs_exact(name, got, ref_lp, exact, rtol, gnorm=0.0, floor=0.0, slack=4.0, kind_rel=None):
     """Parity for tensors whose low-precision *reference* value is itself noisy.
 
     ``exact`` is the same computation in fp64 (reference module in double / oracle in double),
@@ -43,16 +70,18 @@ def check_vs_exact(name, got, ref_lp, exact, rtol, gnorm=0.0, floor=0.0, slack=4
     accumulates its reductions in double -- ATen's acc_type<float, cpu> -- while CUDA code,
     the reference's included, accumulates in float; and two independent roundings of the same
     quantity differ by up to ~2x their individual error; measured worst case over the shipped configs: 3.5x, on
-    an SE excitation weight whose fp32 reference gradient is itself 1.4e-5 off).  Returns (err_got, err_ref) as
-    fractions of ||exact||."""
+    an SE excitation weight whose fp32 reference gradient is itself 1.4e-5 off).  ``kind_rel`` (bf16 tests): the
+    reference's own relative error is taken as the larger of this tensor's and the worst over the blocks' tensors of
+    the same kind (``own_error_by_kind``).  Returns (err_got, err_ref) as fractions of ||exact||."""
     g, r, e = (t.detach().double().cpu() for t in (got, ref_lp, exact))
     assert g.shape == e.shape, (name, g.shape, e.shape)
     assert torch.isfinite(g).all(), f"{name}: non-finite values"
     n = float(e.norm())
     e_got, e_ref = float((g - e).norm()), float((r - e).norm())
-    bound = max(rtol * n + floor * gnorm, slack * e_ref)
+    e_yard = e_ref if kind_rel is None else max(e_ref, kind_rel.get(tensor_kind(name), 0.0) * n)
+    bound = max(rtol * n + floor * gnorm, slack * e_yard)
     assert e_got <= bound, (f"{name}: |got-exact|={e_got:.3e} > max(rtol*|exact|+floor={rtol * n + floor * gnorm:.3e}, "
-                            f"{slack}*|ref-exact|={slack * e_ref:.3e})  (|exact|={n:.3e})")
+                            f"{slack}*|ref-exact|={slack * e_yard:.3e})  (|exact|={n:.3e})")
     d = n if n > 0 else 1.0
     return e_got / d, e_ref / d
 

@@ -10,7 +10,7 @@ import os
 import pytest
 import torch
 
-from parity import check, check_vs_exact, global_norm, rel_err
+from parity import check, check_vs_exact, global_norm, own_error_by_kind, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -98,9 +98,10 @@ def test_fullsize_matches_reference_scalars_and_oracle(case, prec):
     o_out, o_grads = O.loss_and_grads(sd, spec, x, eps, precision=prec, **ref["loss_kwargs"])
     ogn = global_norm(x_grads.values())
     rows, outliers = [], []
+    kind_rel = own_error_by_kind(list(x_grads), o_grads, x_grads) if prec == "bf16" else None
     for k in x_grads:
         try:
-            rows.append((k,) + check_vs_exact(k, grads[k], o_grads[k], x_grads[k], rtol, ogn, floor))
+            rows.append((k,) + check_vs_exact(k, grads[k], o_grads[k], x_grads[k], rtol, ogn, floor, kind_rel=kind_rel))
         except AssertionError as e:
             if prec == "fp32":
                 raise

@@ -17,7 +17,7 @@ Reference: src/models/beta_vae.py:194-272 (loss), src/training/train.py:313-330 
 import pytest
 import torch
 
-from parity import check_vs_exact, global_norm, rel_err, report
+from parity import check_vs_exact, global_norm, own_error_by_kind, rel_err, report
 
 pytestmark = pytest.mark.gpu
 
@@ -81,9 +81,10 @@ def test_graph_replayed_bf16_step_matches_oracle(case):
         assert elp <= rtol, (k, got[k], float(lp_out[k]))
     gn = global_norm(ex_g.values())
     rows, failures = [], []
+    kind_rel = own_error_by_kind(names, lp_g, ex_g)        # the bf16 reference's own noise per kind of tensor
     for k in names:
         try:
-            e_got, e_ref = check_vs_exact(k, grads[k], lp_g[k], ex_g[k], rtol, gn, floor)
+            e_got, e_ref = check_vs_exact(k, grads[k], lp_g[k], ex_g[k], rtol, gn, floor, kind_rel=kind_rel)
         except AssertionError as e:
             failures.append(str(e))
             e_got, e_ref = rel_err(grads[k], ex_g[k]), rel_err(lp_g[k], ex_g[k])
