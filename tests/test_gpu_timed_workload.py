@@ -106,8 +106,9 @@ def test_graph_replayed_bf16_step_matches_oracle(case):
           f"{len(rec['tensors_above_1e-2'])}/{len(rows)} tensors above 1e-2")
     assert not failures, failures
     # whole gradient: 1e-2 where bf16 itself allows it; at this depth the reference under bf16 autocast is itself
-    # ~1.2e-2 from its fp64 evaluation (reported above), so the bound is the larger of the two
-    assert whole <= max(rtol, 1.25 * whole_ref), (whole, whole_ref)
+    # ~1.1-1.2e-2 from its fp64 evaluation (reported above; it moves by ~7 % between hosts, with the reduction order of
+    # the CPU autocast kernels), so the bound is the larger of the two with 1.5x headroom (measured ratio 1.07-1.21)
+    assert whole <= max(rtol, 1.5 * whole_ref), (whole, whole_ref)
 
     # the replay and an un-captured step on the same inputs run the same kernels: bit-identical gradients
     engine.flat_p.copy_(flat_before)
