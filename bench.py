@@ -598,7 +598,7 @@ def cuda_main(args):
         "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": config_key(workload, cfg, batch),
-        "global_batch": batch * world, "parallelism": f"dp{world}" + (f" ({engine.dp_mode} gradient exchange)" if world > 1 else ""),
+        "global_batch": batch * world, "parallelism": f"dp{world}" + (f" ({engine.dp_mode}{'/' + engine._nvls['algo'] if engine._nvls is not None else ''} gradient exchange)" if world > 1 else ""),
         "launch": "eager" if graphed is None else "whole step captured in one CUDA graph",
         "l2": f"no explicit flush: {n_batches} rotating input batches and every step streams its activations "
               f"(y + out of every block, fwd and bwd) through HBM",
