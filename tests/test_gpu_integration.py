@@ -25,12 +25,6 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "beta-vae_b200")
 
-RUNNER = (
-    "import runpy, sys\n"
-    "sys.argv = ['train.py']\n"
-    "runpy.run_path(sys.argv_train, run_name='__main__')\n"
-)
-
 
 def _run(cmd, cwd, env):
     p = subprocess.run(cmd, cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
