@@ -666,7 +666,10 @@ static int wide_f_launch(const FcWide& p, cudaStream_t st) {
 // reparameterise, per-element KL.
 // out[i] = sum_c part[c][i] (fixed order).  32 elements x 8 chunk groups per CTA, four loads in flight per thread;
 // `out` may alias chunk 0 of `part` (element i is only touched by the CTA that owns it).
-__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* part, int nchunks, int n, float* out) {
+// `z` non-null (fc_dec backward): the sum is dz, zeroed where the latent clamp saturated (|z| > clamp) -- the epilogue
+// that used to be its own launch (fcdec_dz_kernel).
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* part, int nchunks, int n, float* out,
+                                                        const float* __restrict__ z = nullptr, float clamp = 0.f) {
   __shared__ float sm[8][32];
   const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
@@ -685,6 +688,7 @@ __global__ void __launch_bounds__(256) chunk_sum_kernel(const float* part, int n
     float v = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) v += sm[g][e];
+    if (z != nullptr && clamp > 0.f && (z[i] < -clamp || z[i] > clamp)) v = 0.f;
     out[i] = v;
   }
 }
@@ -810,17 +814,6 @@ __global__ void heads_db_kernel(const float* __restrict__ D, float* __restrict__
     db_mu[n] = acc;
   else
     db_lv[n - L] = acc;
-}
-
-// dz[b][l] = sum_chunks part[chunk][b][l], zeroed where the latent clamp saturated
-__global__ void fcdec_dz_kernel(const float* __restrict__ part, int nchunks, const float* __restrict__ z, float clamp,
-                                float* __restrict__ dz, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int c = 0; c < nchunks; ++c) acc += part[(size_t)c * n + i];
-    if (clamp > 0.f && (z[i] < -clamp || z[i] > clamp)) acc = 0.f;
-    dz[i] = acc;
-  }
 }
 
 struct HeadsWs {
@@ -988,10 +981,8 @@ extern "C" int bvae_fc_dec_bwd(const void* dh0, const float* z, const void* wd, 
                                : reduce_f_launch<__nv_bfloat16>(dh0, wd, w.part, B, L, F, st);
   if (rc != BVAE_OK) return rc;
   const int n = B * L;
-  chunk_sum_kernel<<<cdiv(n, 32), 256, 0, st>>>(w.part, cdiv(F, RF_CHUNK), n, w.part);
-  BVAE_LAUNCH_CHECK("fcdec_chunk_sum");
-  fcdec_dz_kernel<<<cdiv(n, 256), 256, 0, st>>>(w.part, 1, z, z_clamp, dz, n);
-  BVAE_LAUNCH_CHECK("fcdec_dz");
+  chunk_sum_kernel<<<cdiv(n, 32), 256, 0, st>>>(w.part, cdiv(F, RF_CHUNK), n, dz, z, z_clamp);
+  BVAE_LAUNCH_CHECK("fcdec_chunk_sum_dz");
   // dW[g(f')][l] = sum_b zc[b][l] * dh0[b][f'];  db[g(f')] = sum_b dh0[b][f']  (ones row l == L)
   FcWide p;
   p.A = z; p.a_sm = 1; p.a_sk = L; p.M = L + 1; p.K = B; p.ones_row = L; p.a_clamp = z_clamp;
