@@ -49,12 +49,18 @@ struct Elem<float> {
   static constexpr int kVec = 4;  // elements per 16-byte vector
   __device__ static __forceinline__ float to_f(float v) { return v; }
   __device__ static __forceinline__ float from_f(float v) { return v; }
+  // two neighbours with one store; `p` must be 8-byte aligned
+  __device__ static __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 };
 template <>
 struct Elem<__nv_bfloat16> {
   static constexpr int kVec = 8;
   __device__ static __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
   __device__ static __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  // two neighbours with one store; `p` must be 4-byte aligned
+  __device__ static __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
 };
 
 // 16-byte vector of T, unpacked to / packed from fp32 registers.

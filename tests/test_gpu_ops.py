@@ -108,6 +108,26 @@ def test_conv3x3_fprop_dgrad_wgrad(shape, prec):
         _conv_case(shape, prec.split("-")[0])
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_pack_conv_many_equals_single_packs(prec):
+    """The one-launch tiled pack of all conv layers (bvae_pack_conv_weights: 32 x 32 x 9 tiles through shared memory, two
+    elements per lane) against the element-wise single-layer pack, bit for bit: both layouts, both orientations, full
+    and partial tiles, odd channel counts (single-element stores)."""
+    from bvae_rt import ops
+    dt = ops.BF16 if prec == "bf16" else ops.F32
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 64), (128, 64), (256, 512), (48, 80), (16, 1), (33, 7), (64, 3), (5, 5)]
+    jobs = []
+    for cout, cin in shapes:
+        w = torch.randn(cout, cin, 3, 3, generator=g).cuda()
+        for tr in (False, True):
+            for la in (0, 1):
+                jobs.append((w, tr, la))
+    many = ops.pack_conv_many(jobs, dt)
+    for (w, tr, la), got in zip(jobs, many):
+        assert torch.equal(got, ops.pack_conv(w, dt, tr, la)), (tuple(w.shape), tr, la)
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (3, 32, 16, 128, 64), (2, 16, 32, 64, 128), (1, 32, 32, 256, 256),
                                    (33, 16, 8, 64, 64)])
 def test_conv3x3_fprop_stats_epilogue(shape):
