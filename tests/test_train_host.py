@@ -138,6 +138,9 @@ def _dp_worker(rank, world, port, out, mode):
         assert buckets[0][0].startswith("final_conv") and buckets[-1][-1].startswith("encoder.0")
         eng = TrainEngine(model, lr=1e-3, clip=3.0, dp_mode=mode)   # flat buffers + hooks + bucket plan (CPU tensors)
         assert eng.world == world
+        # the GroupNorm / SE parameter gradients are reduced at the END of backward only when no bucket leaves earlier
+        from bvae_rt import ops
+        assert ops._GN_DEFER["enabled"] == (mode != "buckets")
         # parameters now live in the flat buffer; every gradient slot is a view of flat_g
         for n, p in model.named_parameters():
             o, s, view = eng.slots[n]
@@ -156,6 +159,7 @@ def _dp_worker(rank, world, port, out, mode):
             assert torch.allclose(view, torch.full_like(view, total * coef[n])), n      # SUM over ranks (1/world is folded into Adam)
             assert p.grad.data_ptr() == view.data_ptr()                                  # landed in the bucket, no gather copy
         eng.close()
+        assert ops._GN_DEFER["enabled"]                               # restored for plain autograd use
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
